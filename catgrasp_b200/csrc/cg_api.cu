@@ -1,0 +1,117 @@
+// cg_api.cu -- context management for the C ABI (include/catgrasp_b200.h).
+#include "cg_common.cuh"
+
+extern "C" const char *cg_version(void) { return "catgrasp_b200 0.1 (sm_100a)"; }
+
+extern "C" int cg_ctx_create(int device, cg_ctx **out) {
+  if (!out) return CG_EINVAL;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return CG_ECUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CG_ECUDA;
+  if (prop.major != 10) {
+    // no multi-backend dispatch: this library only carries sm_100a code
+    fprintf(stderr, "catgrasp_b200: device %d is sm_%d%d, this library is sm_100a-only\n", device, prop.major,
+            prop.minor);
+    return CG_EUNSUPPORTED;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return CG_ECUDA;
+  cg_ctx *ctx = new cg_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return CG_ECUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return CG_OK;
+}
+
+extern "C" void cg_ctx_destroy(cg_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->io) cudaFree(ctx->io);
+  if (ctx->hs) cudaFreeHost(ctx->hs);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" int cg_ctx_set_stream(cg_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return CG_EINVAL;
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return CG_OK;
+}
+
+extern "C" int cg_ctx_synchronize(cg_ctx *ctx) {
+  if (!ctx) return CG_EINVAL;
+  CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CG_OK;
+}
+
+extern "C" const char *cg_last_error(cg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t cg_ctx_launch_count(cg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void cg_ctx_reset_launch_count(cg_ctx *ctx) { if (ctx) ctx->launches = 0; }
+
+extern "C" int cg_ctx_set_engine(cg_ctx *ctx, int engine) {
+  if (!ctx) return CG_EINVAL;
+  CG_REQUIRE(ctx, engine == 0 || engine == 1, "engine must be 0 (fp32 SIMT) or 1 (tcgen05)");
+  ctx->engine = engine;
+  return CG_OK;
+}
+extern "C" int cg_ctx_get_engine(cg_ctx *ctx) { return ctx ? ctx->engine : CG_EINVAL; }
+
+static int grow(cg_ctx *ctx, void **p, size_t *cur, size_t bytes, bool host) {
+  if (bytes <= *cur) return CG_OK;
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the arena may still be in use by enqueued work
+  CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*p) {
+    if (host) cudaFreeHost(*p); else cudaFree(*p);
+    *p = nullptr;
+    *cur = 0;
+  }
+  size_t want = bytes + bytes / 4;
+  cudaError_t e = host ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    e = host ? cudaMallocHost(p, want) : cudaMalloc(p, want);
+  }
+  if (e != cudaSuccess) {
+    ctx->err = std::string("workspace allocation failed: ") + cudaGetErrorString(e);
+    cudaGetLastError();
+    return CG_ENOMEM;
+  }
+  *cur = want;
+  return CG_OK;
+}
+
+int cg_ws_reserve(cg_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, false); }
+int cg_io_reserve(cg_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->io, &ctx->io_bytes, bytes, false); }
+int cg_hs_reserve(cg_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->hs, &ctx->hs_bytes, bytes, true); }
+
+extern "C" int cg_ctx_profile(cg_ctx *ctx, int enable) {
+  if (!ctx) return CG_EINVAL;
+  ctx->prof = enable != 0;
+  return CG_OK;
+}
+
+extern "C" int cg_ctx_profile_read(cg_ctx *ctx, double *ms_total, int64_t *launches) {
+  if (!ctx || !ms_total || !launches) return CG_EINVAL;
+  double tot = 0.0;
+  for (auto &pr : ctx->prof_events) {
+    CG_CUDA(ctx, cudaEventSynchronize(pr.second));
+    float ms = 0.f;
+    CG_CUDA(ctx, cudaEventElapsedTime(&ms, pr.first, pr.second));
+    tot += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  *ms_total = tot;
+  *launches = (int64_t)ctx->prof_events.size();
+  ctx->prof_events.clear();
+  return CG_OK;
+}

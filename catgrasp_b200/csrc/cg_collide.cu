@@ -1,0 +1,346 @@
+// cg_collide.cu -- fused grasp-pose filter: pose composition + approach test +
+// lateral-offset search + gripper-SDF collision predicate, one CTA per
+// (grasp pose, symmetry) pair.
+//
+// Pose logic restates my_cpp/common.cpp:159,185-212,253-299 in the reference's
+// fp32 operation order (Eigen 4x4 products without FMA contraction, column
+// normalisation by division through sqrt, the float step accumulator whose 3 mm
+// iteration never executes).  The geometry predicate replaces FCL
+// mesh-vs-octree (collision_manager.cpp:93-111) with the SDF lookups of
+// meshpy/meshpy/sdf.py:292-343 (trilinear) / :377-389 (nearest, in-bounds only):
+// scene points are carried into the posed gripper's SDF grid and the pose
+// collides iff any point has sd < 0.
+//
+// Every floating-point operation below is spelled with an explicit rounding
+// intrinsic so that the CPU oracle (oracle/filter_ref.c) can reproduce the
+// result bit for bit.
+#include "cg_common.cuh"
+
+struct cg_sdf {
+  cg_ctx *ctx;
+  float *grid;  // device, data[i][j][k]
+  int nx, ny, nz;
+  float origin[3];
+  float res;
+};
+
+namespace {
+
+struct SdfView {
+  const float *grid;
+  int nx, ny, nz;
+  float ox, oy, oz;
+  float inv_res;
+};
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+// Eigen fixed-size 4x4 float product as compiled by the reference build (SSE2, no FMA):
+// out(r,c) = ((a(r,0)b(0,c) + a(r,1)b(1,c)) + a(r,2)b(2,c)) + a(r,3)b(3,c)
+__device__ void mm4(const float *A, const float *B, float *O) {
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      float s = mul(A[r * 4 + 0], B[0 * 4 + c]);
+      s = add(s, mul(A[r * 4 + 1], B[1 * 4 + c]));
+      s = add(s, mul(A[r * 4 + 2], B[2 * 4 + c]));
+      s = add(s, mul(A[r * 4 + 3], B[3 * 4 + c]));
+      O[r * 4 + c] = s;
+    }
+}
+
+// Eigen normalize(): v /= sqrt(x*x + y*y + z*z)   (common.cpp:194-197)
+__device__ void normalize_col(float *G, int col) {
+  const float x = G[0 * 4 + col], y = G[1 * 4 + col], z = G[2 * 4 + col];
+  const float n = __fsqrt_rn(add(add(mul(x, x), mul(y, y)), mul(z, z)));
+  G[0 * 4 + col] = __fdiv_rn(x, n);
+  G[1 * 4 + col] = __fdiv_rn(y, n);
+  G[2 * 4 + col] = __fdiv_rn(z, n);
+}
+
+// inverse of the affine map A (3x3 by cofactors, fixed operation order) -> inv[12] = Rinv(9), tinv(3)
+__device__ void affine_inverse(const float *A, float *inv) {
+  const float a = A[0], b = A[1], c = A[2], d = A[4], e = A[5], f = A[6], g = A[8], h = A[9], i = A[10];
+  const float c00 = sub(mul(e, i), mul(f, h));
+  const float c01 = sub(mul(f, g), mul(d, i));
+  const float c02 = sub(mul(d, h), mul(e, g));
+  const float det = add(add(mul(a, c00), mul(b, c01)), mul(c, c02));
+  const float r = __fdiv_rn(1.0f, det);
+  inv[0] = mul(c00, r);
+  inv[1] = mul(sub(mul(c, h), mul(b, i)), r);
+  inv[2] = mul(sub(mul(b, f), mul(c, e)), r);
+  inv[3] = mul(c01, r);
+  inv[4] = mul(sub(mul(a, i), mul(c, g)), r);
+  inv[5] = mul(sub(mul(c, d), mul(a, f)), r);
+  inv[6] = mul(c02, r);
+  inv[7] = mul(sub(mul(b, g), mul(a, h)), r);
+  inv[8] = mul(sub(mul(a, e), mul(b, d)), r);
+  const float tx = A[3], ty = A[7], tz = A[11];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    inv[9 + k] = -add(add(mul(inv[k * 3 + 0], tx), mul(inv[k * 3 + 1], ty)), mul(inv[k * 3 + 2], tz));
+}
+
+__device__ __forceinline__ float sdf_trilinear(const SdfView &s, float gx, float gy, float gz) {
+  // sdf.py:311-343: clip, floor, 8 corners, out-of-bounds corners contribute 0
+  const float cx = fminf(fmaxf(gx, 0.f), (float)(s.nx - 1));
+  const float cy = fminf(fmaxf(gy, 0.f), (float)(s.ny - 1));
+  const float cz = fminf(fmaxf(gz, 0.f), (float)(s.nz - 1));
+  const float lx = floorf(cx), ly = floorf(cy), lz = floorf(cz);
+  const int ix = (int)lx, iy = (int)ly, iz = (int)lz;
+  // weight per axis: 1 - |corner - coord|
+  const float wx0 = sub(1.f, sub(cx, lx)), wx1 = sub(1.f, sub(add(lx, 1.f), cx));
+  const float wy0 = sub(1.f, sub(cy, ly)), wy1 = sub(1.f, sub(add(ly, 1.f), cy));
+  const float wz0 = sub(1.f, sub(cz, lz)), wz1 = sub(1.f, sub(add(lz, 1.f), cz));
+  const bool hx = (ix + 1) < s.nx, hy = (iy + 1) < s.ny, hz = (iz + 1) < s.nz;
+  const size_t sx = (size_t)s.ny * s.nz, sy = (size_t)s.nz;
+  const float *p = s.grid + (size_t)ix * sx + (size_t)iy * sy + iz;
+  // corner order of Sdf3D (sdf.py:217-225): i -> (x,y,z) in {min,max}
+  //   0:(0,0,0) 1:(1,0,0) 2:(0,1,0) 3:(0,0,1) 4:(1,1,0) 5:(0,1,1) 6:(1,0,1) 7:(1,1,1)
+  const float v0 = __ldg(p);
+  const float v1 = hx ? __ldg(p + sx) : 0.f;
+  const float v2 = hy ? __ldg(p + sy) : 0.f;
+  const float v3 = hz ? __ldg(p + 1) : 0.f;
+  const float v4 = (hx && hy) ? __ldg(p + sx + sy) : 0.f;
+  const float v5 = (hy && hz) ? __ldg(p + sy + 1) : 0.f;
+  const float v6 = (hx && hz) ? __ldg(p + sx + 1) : 0.f;
+  const float v7 = (hx && hy && hz) ? __ldg(p + sx + sy + 1) : 0.f;
+  float sd = 0.f;
+  sd = fmaf(mul(mul(wx0, wy0), wz0), v0, sd);
+  sd = fmaf(mul(mul(wx1, wy0), wz0), v1, sd);
+  sd = fmaf(mul(mul(wx0, wy1), wz0), v2, sd);
+  sd = fmaf(mul(mul(wx0, wy0), wz1), v3, sd);
+  sd = fmaf(mul(mul(wx1, wy1), wz0), v4, sd);
+  sd = fmaf(mul(mul(wx0, wy1), wz1), v5, sd);
+  sd = fmaf(mul(mul(wx1, wy0), wz1), v6, sd);
+  sd = fmaf(mul(mul(wx1, wy1), wz1), v7, sd);
+  return sd;
+}
+
+// nearest cell; *inb = false when the rounded cell is outside the grid
+__device__ __forceinline__ float sdf_nearest(const SdfView &s, float gx, float gy, float gz, bool clamp, bool *inb) {
+  float rx = rintf(gx), ry = rintf(gy), rz = rintf(gz);  // np.round / torch.round: half to even
+  bool ok = (rx >= 0.f) && (rx < (float)s.nx) && (ry >= 0.f) && (ry < (float)s.ny) && (rz >= 0.f) && (rz < (float)s.nz);
+  if (!ok) {
+    if (!clamp) { *inb = false; return 0.f; }
+    rx = fminf(fmaxf(rx, 0.f), (float)(s.nx - 1));
+    ry = fminf(fmaxf(ry, 0.f), (float)(s.ny - 1));
+    rz = fminf(fmaxf(rz, 0.f), (float)(s.nz - 1));
+  }
+  *inb = true;
+  return __ldg(s.grid + ((size_t)(int)rx * s.ny + (int)ry) * s.nz + (int)rz);
+}
+
+// true iff point x (camera frame) lies inside the posed gripper: sd(grid(inv * x)) < 0
+__device__ __forceinline__ bool point_hits(const SdfView &s, const float *inv, int mode, float x, float y, float z) {
+  const float qx = fmaf(inv[2], z, fmaf(inv[1], y, fmaf(inv[0], x, inv[9])));
+  const float qy = fmaf(inv[5], z, fmaf(inv[4], y, fmaf(inv[3], x, inv[10])));
+  const float qz = fmaf(inv[8], z, fmaf(inv[7], y, fmaf(inv[6], x, inv[11])));
+  const float gx = mul(sub(qx, s.ox), s.inv_res);   // sdf.py:252-264
+  const float gy = mul(sub(qy, s.oy), s.inv_res);
+  const float gz = mul(sub(qz, s.oz), s.inv_res);
+  if (mode == CG_SDF_TRILINEAR) return sdf_trilinear(s, gx, gy, gz) < 0.f;
+  bool inb;
+  const float sd = sdf_nearest(s, gx, gy, gz, false, &inb);
+  return inb && (sd < 0.f);
+}
+
+constexpr int FT = 256;
+
+__device__ bool any_point_hits(const SdfView &s, const float *inv, int mode, const float *__restrict__ pts, int P,
+                               volatile int *flag) {
+  bool hit = false;
+  int it = 0;
+  for (int p = threadIdx.x; p < P; p += FT, it++) {
+    if ((it & 7) == 7 && *flag) break;  // another thread already found a collision
+    const float x = __ldg(pts + 3 * (size_t)p), y = __ldg(pts + 3 * (size_t)p + 1), z = __ldg(pts + 3 * (size_t)p + 2);
+    if (point_hits(s, inv, mode, x, y, z)) {
+      hit = true;
+      *flag = 1;
+      break;
+    }
+  }
+  return __syncthreads_or(hit) != 0;
+}
+
+__global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, const float *__restrict__ grasp_poses,
+                                                    int G, const float *__restrict__ sym, int S, SdfView sdf_open,
+                                                    const float *__restrict__ open_pts, int P1, SdfView sdf_encl,
+                                                    const float *__restrict__ encl_pts, int P2,
+                                                    uint8_t *__restrict__ out_status, int8_t *__restrict__ out_offset,
+                                                    float *__restrict__ out_poses) {
+  __shared__ float g_s[16];      // grasp_in_cam (normalised)
+  __shared__ float cur_s[16];    // shifted candidate
+  __shared__ float inv_s[12];
+  __shared__ int rej_dir;
+  __shared__ int flag;
+  const long q = blockIdx.x;
+  const int i = (int)(q / S), j = (int)(q % S);
+  if (threadIdx.x == 0) {
+    float c2c[16], tmp[16], g[16];
+    mm4(prm.nocs_pose, prm.canonical_to_nocs, c2c);            // common.cpp:159
+    mm4(sym + (size_t)j * 16, grasp_poses + (size_t)i * 16, tmp);  // :190
+    mm4(c2c, tmp, g);                                          // :191
+    for (int col = 0; col < 3; col++) normalize_col(g, col);   // :194-197
+    int rd = 0;
+    if (prm.filter_approach_dir_face_camera) {                 // :199-212
+      const float x = g[0], y = g[4], z = g[8];
+      const float n = __fsqrt_rn(add(add(mul(x, x), mul(y, y)), mul(z, z)));
+      const float zz = __fdiv_rn(z, n);
+      // dot with (0,0,1): x*0 + y*0 + z*1
+      const float dot = add(add(mul(__fdiv_rn(x, n), 0.f), mul(__fdiv_rn(y, n), 0.f)), mul(zz, 1.f));
+      rd = dot < 0.f;
+    }
+    rej_dir = rd;
+    for (int k = 0; k < 16; k++) g_s[k] = g[k];
+  }
+  __syncthreads();
+  if (rej_dir) {
+    if (threadIdx.x == 0) { out_status[q] = CG_ST_REJ_DIR; out_offset[q] = -1; }
+    if (threadIdx.x < 16) out_poses[q * 16 + threadIdx.x] = 0.f;
+    return;
+  }
+  // float accumulator of common.cpp:255: 0, 0.001f, 0.001f+0.001f (the 3 mm step never runs)
+  const float step1 = 0.001f;
+  const float step2 = __fadd_rn(step1, 0.001f);
+  const int n_off = prm.adjust_collision_pose ? 5 : 1;
+  int winner = -1;
+  for (int k = 0; k < n_off; k++) {
+    if (threadIdx.x == 0) {
+      const float step = (k == 0) ? 0.f : ((k <= 2) ? step1 : step2);
+      const float sign = (k == 0 || (k & 1)) ? 1.f : -1.f;   // order (0,+),(1,+),(1,-),(2,+),(2,-)
+      float cur[16], gic[16];
+      for (int e = 0; e < 16; e++) cur[e] = g_s[e];
+      for (int r = 0; r < 3; r++)                              // :265  t += (step*major_dir)*sign
+        cur[r * 4 + 3] = add(cur[r * 4 + 3], mul(mul(step, g_s[r * 4 + 1]), sign));
+      mm4(cur, prm.gripper_in_grasp, gic);                     // :266
+      affine_inverse(gic, inv_s);
+      for (int e = 0; e < 16; e++) cur_s[e] = cur[e];
+      flag = 0;
+    }
+    __syncthreads();
+    bool coll = any_point_hits(sdf_open, inv_s, prm.sdf_mode, open_pts, P1, &flag);
+    if (!coll && P2 > 0) coll = any_point_hits(sdf_encl, inv_s, prm.sdf_mode, encl_pts, P2, &flag);
+    if (!coll) { winner = k; break; }
+    __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
+  }
+  if (threadIdx.x == 0) {
+    out_status[q] = (winner >= 0) ? CG_ST_ACCEPT : CG_ST_REJ_COLL;
+    out_offset[q] = (int8_t)winner;
+  }
+  if (threadIdx.x < 16) out_poses[q * 16 + threadIdx.x] = (winner >= 0) ? cur_s[threadIdx.x] : 0.f;
+}
+
+__global__ void sdf_lookup_kernel(SdfView s, const float *__restrict__ gc, int P, int mode, float *__restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float gx = gc[3 * (size_t)p], gy = gc[3 * (size_t)p + 1], gz = gc[3 * (size_t)p + 2];
+  if (mode == CG_SDF_TRILINEAR) {
+    out[p] = sdf_trilinear(s, gx, gy, gz);
+  } else {
+    bool inb;
+    out[p] = sdf_nearest(s, gx, gy, gz, true, &inb);  // sdf.py:352-358 clamps
+  }
+}
+
+SdfView make_view(const cg_sdf *s) {
+  SdfView v;
+  v.grid = s->grid; v.nx = s->nx; v.ny = s->ny; v.nz = s->nz;
+  v.ox = s->origin[0]; v.oy = s->origin[1]; v.oz = s->origin[2];
+  v.inv_res = 1.0f / s->res;
+  return v;
+}
+
+}  // namespace
+
+extern "C" int cg_sdf_create(cg_ctx *ctx, const float *grid_host, int nx, int ny, int nz, const float origin[3],
+                             float resolution, cg_sdf **out) {
+  if (!ctx || !out) return CG_EINVAL;
+  CG_REQUIRE(ctx, grid_host && nx > 0 && ny > 0 && nz > 0 && resolution > 0.f, "sdf: bad grid");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cg_sdf *s = new cg_sdf();
+  s->ctx = ctx; s->nx = nx; s->ny = ny; s->nz = nz; s->res = resolution;
+  for (int k = 0; k < 3; k++) s->origin[k] = origin[k];
+  const size_t bytes = (size_t)nx * ny * nz * sizeof(float);
+  CG_CUDA(ctx, cudaMalloc(&s->grid, bytes));
+  CG_CUDA(ctx, cudaMemcpyAsync(s->grid, grid_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = s;
+  return CG_OK;
+}
+
+extern "C" void cg_sdf_destroy(cg_sdf *sdf) {
+  if (!sdf) return;
+  cudaSetDevice(sdf->ctx->device);
+  cudaFree(sdf->grid);
+  delete sdf;
+}
+
+extern "C" int cg_sdf_lookup_dev(cg_sdf *sdf, const float *grid_coords, int P, int mode, float *out_sd) {
+  if (!sdf) return CG_EINVAL;
+  cg_ctx *ctx = sdf->ctx;
+  CG_REQUIRE(ctx, grid_coords && out_sd && P > 0, "sdf_lookup: bad arguments");
+  CG_REQUIRE(ctx, mode == CG_SDF_TRILINEAR || mode == CG_SDF_NEAREST, "sdf_lookup: mode");
+  sdf_lookup_kernel<<<(P + 255) / 256, 256, 0, ctx->stream>>>(make_view(sdf), grid_coords, P, mode, out_sd);
+  CG_LAUNCH_CHECK(ctx);
+  return CG_OK;
+}
+
+extern "C" int cg_filter_grasp_pose_dev(cg_ctx *ctx, const cg_filter_params *prm, const float *grasp_poses, int G,
+                                        const float *symmetry_tfs, int S, cg_sdf *sdf_open, const float *open_pts,
+                                        int P1, cg_sdf *sdf_enclosed, const float *enclosed_pts, int P2,
+                                        uint8_t *out_status, int8_t *out_offset, float *out_poses) {
+  if (!ctx) return CG_EINVAL;
+  CG_REQUIRE(ctx, prm && grasp_poses && symmetry_tfs && G > 0 && S > 0, "filter: poses");
+  CG_REQUIRE(ctx, sdf_open && (P1 == 0 || open_pts) && P1 >= 0, "filter: open gripper sdf/points");
+  CG_REQUIRE(ctx, P2 == 0 || (sdf_enclosed && enclosed_pts), "filter: enclosed gripper sdf/points");
+  CG_REQUIRE(ctx, out_status && out_offset && out_poses, "filter: outputs");
+  CG_REQUIRE(ctx, prm->sdf_mode == CG_SDF_TRILINEAR || prm->sdf_mode == CG_SDF_NEAREST, "filter: sdf_mode");
+  CG_REQUIRE(ctx, (long)G * S < 2147483647L, "filter: too many pairs");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  SdfView vo = make_view(sdf_open);
+  SdfView ve = sdf_enclosed ? make_view(sdf_enclosed) : vo;
+  filter_kernel<<<(unsigned)((long)G * S), FT, 0, ctx->stream>>>(*prm, grasp_poses, G, symmetry_tfs, S, vo, open_pts,
+                                                                 P1, ve, enclosed_pts, P2, out_status, out_offset,
+                                                                 out_poses);
+  CG_LAUNCH_CHECK(ctx);
+  return CG_OK;
+}
+
+extern "C" int cg_filter_grasp_pose_host(cg_ctx *ctx, const cg_filter_params *prm, const float *grasp_poses, int G,
+                                         const float *symmetry_tfs, int S, cg_sdf *sdf_open, const float *open_pts,
+                                         int P1, cg_sdf *sdf_enclosed, const float *enclosed_pts, int P2,
+                                         uint8_t *out_status, int8_t *out_offset, float *out_poses) {
+  if (!ctx) return CG_EINVAL;
+  CG_REQUIRE(ctx, prm && grasp_poses && symmetry_tfs && G > 0 && S > 0, "filter_host: poses");
+  CG_REQUIRE(ctx, out_status && out_offset && out_poses, "filter_host: outputs");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t Q = (size_t)G * S;
+  const size_t need = cg_arena::pad((size_t)G * 64) + cg_arena::pad((size_t)S * 64) + cg_arena::pad((size_t)P1 * 12) +
+                      cg_arena::pad((size_t)P2 * 12) + cg_arena::pad(Q) * 2 + cg_arena::pad(Q * 64) + 4096;
+  int rc = cg_io_reserve(ctx, need);
+  if (rc) return rc;
+  cg_arena ar(ctx->io);
+  float *d_g = ar.take<float>((size_t)G * 16);
+  float *d_s = ar.take<float>((size_t)S * 16);
+  float *d_p1 = ar.take<float>((size_t)P1 * 3 + 1);
+  float *d_p2 = ar.take<float>((size_t)P2 * 3 + 1);
+  uint8_t *d_st = ar.take<uint8_t>(Q);
+  int8_t *d_of = ar.take<int8_t>(Q);
+  float *d_po = ar.take<float>(Q * 16);
+  cudaStream_t st = ctx->stream;
+  CG_CUDA(ctx, cudaMemcpyAsync(d_g, grasp_poses, (size_t)G * 64, cudaMemcpyHostToDevice, st));
+  CG_CUDA(ctx, cudaMemcpyAsync(d_s, symmetry_tfs, (size_t)S * 64, cudaMemcpyHostToDevice, st));
+  if (P1 > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_p1, open_pts, (size_t)P1 * 12, cudaMemcpyHostToDevice, st));
+  if (P2 > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_p2, enclosed_pts, (size_t)P2 * 12, cudaMemcpyHostToDevice, st));
+  rc = cg_filter_grasp_pose_dev(ctx, prm, d_g, G, d_s, S, sdf_open, d_p1, P1, sdf_enclosed, d_p2, P2, d_st, d_of, d_po);
+  if (rc) return rc;
+  CG_CUDA(ctx, cudaMemcpyAsync(out_status, d_st, Q, cudaMemcpyDeviceToHost, st));
+  CG_CUDA(ctx, cudaMemcpyAsync(out_offset, d_of, Q, cudaMemcpyDeviceToHost, st));
+  CG_CUDA(ctx, cudaMemcpyAsync(out_poses, d_po, Q * 64, cudaMemcpyDeviceToHost, st));
+  CG_CUDA(ctx, cudaStreamSynchronize(st));
+  return CG_OK;
+}

@@ -1,0 +1,176 @@
+// cg_linear.cu -- batched fully-connected layers and the small epilogue kernels
+// of the PointNet heads (fp32 SIMT; < 1% of the path's FLOPs).
+//
+//   Y[M][N] = act( X[M][K] @ Wt[K][N] + bias[row / bias_row_div][N] )
+//
+// replaces nn.Linear / nn.Conv1d(k=1) + folded BatchNorm + ReLU of
+// pointnet2.py:176-183, :214-221, :295-298 and the PointNetSeg head :323-327.
+#include "cg_net.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) linear_kernel(const float *__restrict__ X, int M, int K,
+                                                      const float *__restrict__ Wt,
+                                                      const float *__restrict__ bias, int N, int relu,
+                                                      int bias_row_div, int x_is_keys,
+                                                      float *__restrict__ Y) {
+  __shared__ __align__(16) float xs[BK][BM + 4];
+  __shared__ __align__(16) float ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // X tile: 64 rows x 16 k  (each thread: one row, 4 consecutive k)
+    {
+      const int r = tid >> 2, kq = (tid & 3) * 4;
+      const int m = m0 + r;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (m < M) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int k = k0 + kq + q;
+          if (k < K) {
+            float f = X[(size_t)m * K + k];
+            if (x_is_keys) f = cg_key2f(__float_as_uint(f));
+            v[q] = f;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) xs[kq + q][r] = v[q];
+    }
+    // W tile: 16 k x 64 n  (each thread: one k row, 4 consecutive n)
+    {
+      const int r = tid >> 4, nq = (tid & 15) * 4;
+      const int k = k0 + r;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int n = n0 + nq + q;
+        ws[r][nq + q] = (k < K && n < N) ? Wt[(size_t)k * N + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      const float4 a = *reinterpret_cast<const float4 *>(&xs[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4 *>(&ws[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const float *brow = bias ? (bias + (size_t)(bias_row_div > 0 ? (m / bias_row_div) : 0) * N) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (brow ? brow[n] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      Y[(size_t)m * N + n] = v;
+    }
+  }
+}
+
+// softmax over C <= 32 classes, one warp per row (predicter.py:86-90)
+__global__ void softmax_kernel(const float *__restrict__ logits, int B, int C, float *__restrict__ probs,
+                               int32_t *__restrict__ label) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float v = (lane < C) ? logits[(size_t)row * C + lane] : -INFINITY;
+  float m = v;
+  int am = (lane < C) ? lane : 0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  const float e = (lane < C) ? expf(v - m) : 0.f;
+  float s = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane < C && probs) probs[(size_t)row * C + lane] = e / s;
+  if (lane == 0 && label) label[row] = am;
+}
+
+// NUNOCS post-processing (predicter.py:144-150): one warp per (point, axis)
+__global__ void nunocs_post_kernel(const float *__restrict__ logits, int P, int bins,
+                                   float *__restrict__ coords, float *__restrict__ conf_z,
+                                   int32_t *__restrict__ out_bins) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= P * 3) return;
+  const int p = w / 3, ax = w % 3;
+  const float *row = logits + (size_t)p * 3 * bins + (size_t)ax * bins;
+  float m = -INFINITY;
+  int am = 0x7fffffff;
+  for (int k = lane; k < bins; k += 32) {
+    const float v = row[k];
+    if (v > m) { m = v; am = k; }   // strict: first maximum wins inside a lane
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+    if (om > m || (om == m && oa < am)) { m = om; am = oa; }
+  }
+  if (lane == 0) {
+    const float res = 1.0f / (float)bins;          // bin_resolution, predicter.py:145
+    if (coords) coords[(size_t)p * 3 + ax] = (float)am * res - 0.5f;  // :146,:150
+    if (out_bins) out_bins[(size_t)p * 3 + ax] = am;
+  }
+  if (ax == 2 && conf_z) {
+    float s = 0.f;
+    for (int k = lane; k < bins; k += 32) s += expf(row[k] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) conf_z[p] = 1.0f / s;           // softmax prob at the argmax, :147-148
+  }
+}
+
+}  // namespace
+
+int cg_linear_launch(cg_ctx *ctx, const float *X, int M, int K, const float *Wt, const float *bias, int N,
+                     int relu, int bias_row_div, int x_is_keys, float *Y) {
+  CG_REQUIRE(ctx, M > 0 && K > 0 && N > 0, "linear: bad shape");
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  linear_kernel<<<grid, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
+  CG_LAUNCH_CHECK(ctx);
+  return CG_OK;
+}
+
+int cg_softmax_launch(cg_ctx *ctx, const float *logits, int B, int C, float *probs, int32_t *label) {
+  CG_REQUIRE(ctx, C >= 1 && C <= 32, "softmax: 1 <= n_out <= 32");
+  const int wpb = 8;
+  softmax_kernel<<<(B + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(logits, B, C, probs, label);
+  CG_LAUNCH_CHECK(ctx);
+  return CG_OK;
+}
+
+int cg_nunocs_post_launch(cg_ctx *ctx, const float *logits, int P, int bins, float *coords, float *conf_z,
+                          int32_t *out_bins) {
+  CG_REQUIRE(ctx, P > 0 && bins > 0, "nunocs_post: bad shape");
+  const int wpb = 8;
+  const long warps = (long)P * 3;
+  nunocs_post_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(logits, P, bins, coords,
+                                                                                     conf_z, out_bins);
+  CG_LAUNCH_CHECK(ctx);
+  return CG_OK;
+}

@@ -1,0 +1,346 @@
+// cg_net.cu -- network handles and forward orchestration behind the C ABI.
+//
+// PointNetCls  (pointnet2.py:275-299): trunk A -> FC x3 -> T3
+//                                      trunk B -> FC x3 -> T64
+//                                      trunk C -> FC x3 -> logits -> softmax
+// PointNetSeg  (pointnet2.py:302-329): same encoder, trunk C also emits the
+//   64-ch point feature; the 1088->512 conv is split into its global part
+//   (computed once per cloud and used as a per-cloud bias) and its 64-ch
+//   point part, which removes 4.29 of 9.72 GMAC without changing the math.
+#include "cg_net.cuh"
+
+namespace {
+
+struct LayerDim { int K, C; };
+
+void layer_dims(int kind, int n_out, LayerDim d[L_COUNT]) {
+  d[L_S3_C1] = {6, 64};     d[L_S3_C2] = {64, 128};   d[L_S3_C3] = {128, 1024};
+  d[L_S3_F1] = {1024, 512}; d[L_S3_F2] = {512, 256};  d[L_S3_F3] = {256, 9};
+  d[L_E_C1] = {6, 64};
+  d[L_SK_C1] = {64, 64};    d[L_SK_C2] = {64, 128};   d[L_SK_C3] = {128, 1024};
+  d[L_SK_F1] = {1024, 512}; d[L_SK_F2] = {512, 256};  d[L_SK_F3] = {256, 4096};
+  d[L_E_C2] = {64, 128};    d[L_E_C3] = {128, 1024};
+  if (kind == CG_NET_CLS) {
+    d[L_HEAD0] = {1024, 512}; d[L_HEAD1] = {512, 256}; d[L_HEAD2] = {256, n_out};
+    d[L_HEAD3] = {0, 0};      d[L_HEAD4] = {0, 0};
+  } else {
+    d[L_HEAD0] = {1024, 512}; d[L_HEAD1] = {64, 512};  d[L_HEAD2] = {512, 256};
+    d[L_HEAD3] = {256, 128};  d[L_HEAD4] = {128, n_out};
+  }
+}
+
+inline size_t pad64(size_t n) { return (n + 63) & ~size_t(63); }
+
+constexpr int CHUNK_B = 16384;  // candidates per internal pass (bounds the T64 workspace to 256 MB)
+
+}  // namespace
+
+extern "C" size_t cg_net_blob_floats(int kind, int n_out) {
+  LayerDim d[L_COUNT];
+  layer_dims(kind, n_out, d);
+  size_t n = 0;
+  for (int i = 0; i < L_COUNT; i++) n += pad64((size_t)d[i].K * d[i].C) + pad64((size_t)d[i].C);
+  return n;
+}
+
+extern "C" int cg_net_create(cg_ctx *ctx, int kind, int n_out, const float *blob_host, size_t blob_floats,
+                             cg_net **out) {
+  if (!ctx || !out) return CG_EINVAL;
+  CG_REQUIRE(ctx, kind == CG_NET_CLS || kind == CG_NET_SEG, "net kind");
+  CG_REQUIRE(ctx, n_out > 0 && (kind == CG_NET_SEG || n_out <= 32), "n_out");
+  CG_REQUIRE(ctx, blob_host && blob_floats == cg_net_blob_floats(kind, n_out), "weight blob size mismatch");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  cg_net *net = new cg_net();
+  net->ctx = ctx;
+  net->kind = kind;
+  net->n_out = n_out;
+  net->blob_floats = blob_floats;
+  for (int i = 0; i < 3; i++) net->tc_w3[i] = nullptr;
+  CG_CUDA(ctx, cudaMalloc(&net->blob_dev, blob_floats * sizeof(float)));
+  CG_CUDA(ctx, cudaMemcpyAsync(net->blob_dev, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice,
+                               ctx->stream));
+  LayerDim d[L_COUNT];
+  layer_dims(kind, n_out, d);
+  size_t off = 0;
+  size_t w3_off[3];
+  for (int i = 0; i < L_COUNT; i++) {
+    net->L[i].K = d[i].K;
+    net->L[i].C = d[i].C;
+    net->L[i].Wt = net->blob_dev + off;
+    if (i == L_S3_C3) w3_off[0] = off;
+    if (i == L_SK_C3) w3_off[1] = off;
+    if (i == L_E_C3) w3_off[2] = off;
+    off += pad64((size_t)d[i].K * d[i].C);
+    net->L[i].b = net->blob_dev + off;
+    off += pad64((size_t)d[i].C);
+  }
+  // tensor-core operand images of the three 128->1024 layers
+  for (int i = 0; i < 3; i++) {
+    CG_CUDA(ctx, cudaMalloc(&net->tc_w3[i], cg_tc_w3_bytes()));
+    int rc = cg_tc_prepare_w3(ctx, blob_host + w3_off[i], net->tc_w3[i]);
+    if (rc != CG_OK) return rc;
+  }
+  CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = net;
+  return CG_OK;
+}
+
+extern "C" void cg_net_destroy(cg_net *net) {
+  if (!net) return;
+  cudaSetDevice(net->ctx->device);
+  cudaFree(net->blob_dev);
+  for (int i = 0; i < 3; i++) cudaFree(net->tc_w3[i]);
+  delete net;
+}
+
+namespace {
+
+int trunk_launch(cg_ctx *ctx, const cg_trunk_args &a) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->prof) {
+    CG_CUDA(ctx, cudaEventCreate(&e0));
+    CG_CUDA(ctx, cudaEventCreate(&e1));
+    CG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  }
+  const int rc = ctx->engine == 1 ? cg_trunk_launch_tc(ctx, a) : cg_trunk_launch_simt(ctx, a);
+  if (ctx->prof) {
+    CG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    ctx->prof_events.emplace_back(e0, e1);
+  }
+  return rc;
+}
+
+struct EncoderWs {
+  uint32_t *gmax;   // (B,1024)
+  float *f1;        // (B,512)
+  float *f2;        // (B,256)
+  float *T3;        // (B,9)
+  float *T64;       // (B,4096)
+};
+
+size_t encoder_ws_bytes(int B) {
+  return cg_arena::pad((size_t)B * 1024 * 4) + cg_arena::pad((size_t)B * 512 * 4) +
+         cg_arena::pad((size_t)B * 256 * 4) + cg_arena::pad((size_t)B * 9 * 4) +
+         cg_arena::pad((size_t)B * 4096 * 4) + 4096;
+}
+
+void encoder_ws_carve(cg_arena &ar, int B, EncoderWs &w) {
+  w.gmax = ar.take<uint32_t>((size_t)B * 1024);
+  w.f1 = ar.take<float>((size_t)B * 512);
+  w.f2 = ar.take<float>((size_t)B * 256);
+  w.T3 = ar.take<float>((size_t)B * 9);
+  w.T64 = ar.take<float>((size_t)B * 4096);
+}
+
+// Runs the PointNetEncoder (pointnet2.py:241-271) for B clouds; on return w.gmax holds the
+// (B,1024) global feature as order-preserving keys; pf_out (optional) the 64-ch point feature.
+int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs &w, float *pf_out) {
+  cg_ctx *ctx = net->ctx;
+  const cg_layer *L = net->L;
+  int rc;
+  cg_trunk_args a;
+  a.in = in; a.B = B; a.N = N;
+  // --- trunk A: STN3d convs + max (pointnet2.py:170-175)
+  CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
+  a.T3 = nullptr; a.l0 = L[L_S3_C1]; a.stage1_mode = 0; a.l1 = cg_layer{nullptr, nullptr, 0, 0}; a.T64 = nullptr;
+  a.l2 = L[L_S3_C2]; a.l3 = L[L_S3_C3]; a.l3_tc = net->tc_w3[0]; a.relu3 = 1; a.gmax_keys = w.gmax; a.pf_out = nullptr;
+  if ((rc = trunk_launch(ctx, a))) return rc;
+  if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_S3_F1].Wt, L[L_S3_F1].b, 512, 1, 0, 1, w.f1))) return rc;
+  if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_S3_F2].Wt, L[L_S3_F2].b, 256, 1, 0, 0, w.f2))) return rc;
+  if ((rc = cg_linear_launch(ctx, w.f2, B, 256, L[L_S3_F3].Wt, L[L_S3_F3].b, 9, 0, 0, 0, w.T3))) return rc;
+  // --- trunk B: encoder conv1 + STNkd convs + max (pointnet2.py:252, :208-213)
+  CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
+  a.T3 = w.T3; a.l0 = L[L_E_C1]; a.stage1_mode = 1; a.l1 = L[L_SK_C1];
+  a.l2 = L[L_SK_C2]; a.l3 = L[L_SK_C3]; a.l3_tc = net->tc_w3[1]; a.relu3 = 1;
+  if ((rc = trunk_launch(ctx, a))) return rc;
+  if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_SK_F1].Wt, L[L_SK_F1].b, 512, 1, 0, 1, w.f1))) return rc;
+  if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_SK_F2].Wt, L[L_SK_F2].b, 256, 1, 0, 0, w.f2))) return rc;
+  if ((rc = cg_linear_launch(ctx, w.f2, B, 256, L[L_SK_F3].Wt, L[L_SK_F3].b, 4096, 0, 0, 0, w.T64))) return rc;
+  // --- trunk C: conv1, @T64, conv2, conv3(+BN, no ReLU), max (pointnet2.py:252-265)
+  CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
+  a.stage1_mode = 2; a.T64 = w.T64; a.l1 = cg_layer{nullptr, nullptr, 64, 64};
+  a.l2 = L[L_E_C2]; a.l3 = L[L_E_C3]; a.l3_tc = net->tc_w3[2]; a.relu3 = 0; a.pf_out = pf_out;
+  if ((rc = trunk_launch(ctx, a))) return rc;
+  return CG_OK;
+}
+
+int cls_forward_impl(cg_net *net, const cg_input_src &in_all, int B_all, int N, float *out_logits, float *out_probs,
+                     int32_t *out_label) {
+  cg_ctx *ctx = net->ctx;
+  CG_REQUIRE(ctx, net->kind == CG_NET_CLS, "net is not a PointNetCls");
+  CG_REQUIRE(ctx, B_all > 0 && N > 0, "B,N must be positive");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n_out = net->n_out;
+  const int Bc_max = B_all < CHUNK_B ? B_all : CHUNK_B;
+  const size_t need = encoder_ws_bytes(Bc_max) + cg_arena::pad((size_t)Bc_max * n_out * 4) + 1024;
+  int rc = cg_ws_reserve(ctx, need);
+  if (rc) return rc;
+  for (int b0 = 0; b0 < B_all; b0 += CHUNK_B) {
+    const int B = (B_all - b0 < CHUNK_B) ? (B_all - b0) : CHUNK_B;
+    cg_arena ar(ctx->ws);
+    EncoderWs w;
+    encoder_ws_carve(ar, B, w);
+    float *logits_ws = ar.take<float>((size_t)B * n_out);
+    cg_input_src in = in_all;
+    if (in.x_direct) in.x_direct += (size_t)b0 * N * 6;
+    if (in.poses) in.poses += (size_t)b0 * 16;
+    if (in.ids) in.ids += (size_t)b0 * N;
+    if ((rc = encoder_forward(net, in, B, N, w, nullptr))) return rc;
+    const cg_layer *L = net->L;
+    if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_HEAD0].Wt, L[L_HEAD0].b, 512, 1, 0, 1, w.f1))) return rc;
+    if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_HEAD1].Wt, L[L_HEAD1].b, 256, 1, 0, 0, w.f2))) return rc;
+    float *lg = out_logits ? out_logits + (size_t)b0 * n_out : logits_ws;
+    if ((rc = cg_linear_launch(ctx, w.f2, B, 256, L[L_HEAD2].Wt, L[L_HEAD2].b, n_out, 0, 0, 0, lg))) return rc;
+    if (out_probs || out_label) {
+      if ((rc = cg_softmax_launch(ctx, lg, B, n_out, out_probs ? out_probs + (size_t)b0 * n_out : nullptr,
+                                  out_label ? out_label + b0 : nullptr)))
+        return rc;
+    }
+  }
+  return CG_OK;
+}
+
+int seg_forward_impl(cg_net *net, const float *x, int B, int N, float *out_logits, int bins, float *out_coords,
+                     float *out_conf, int32_t *out_bins) {
+  cg_ctx *ctx = net->ctx;
+  CG_REQUIRE(ctx, net->kind == CG_NET_SEG, "net is not a PointNetSeg");
+  CG_REQUIRE(ctx, B > 0 && N > 0 && x, "seg: bad arguments");
+  CG_REQUIRE(ctx, B <= CHUNK_B, "seg: too many clouds in one call");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t P = (size_t)B * N;
+  const int n_out = net->n_out;
+  const size_t need = encoder_ws_bytes(B) + cg_arena::pad(P * 64 * 4) + cg_arena::pad((size_t)B * 512 * 4) +
+                      cg_arena::pad(P * 512 * 4) + cg_arena::pad(P * 256 * 4) + cg_arena::pad(P * 128 * 4) +
+                      cg_arena::pad(P * n_out * 4) + 4096;
+  int rc = cg_ws_reserve(ctx, need);
+  if (rc) return rc;
+  cg_arena ar(ctx->ws);
+  EncoderWs w;
+  encoder_ws_carve(ar, B, w);
+  float *pf = ar.take<float>(P * 64);
+  float *biasg = ar.take<float>((size_t)B * 512);
+  float *y1 = ar.take<float>(P * 512);
+  float *y2 = ar.take<float>(P * 256);
+  float *y3 = ar.take<float>(P * 128);
+  float *lg = out_logits ? out_logits : ar.take<float>(P * n_out);
+  cg_input_src in;
+  memset(&in, 0, sizeof(in));
+  in.x_direct = x;
+  if ((rc = encoder_forward(net, in, B, N, w, pf))) return rc;
+  const cg_layer *L = net->L;
+  // global half of conv1 (pointnet2.py:270-271 tiles the global feature over N; it is constant per cloud)
+  if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_HEAD0].Wt, L[L_HEAD0].b, 512, 0, 0, 1, biasg))) return rc;
+  if ((rc = cg_linear_launch(ctx, pf, (int)P, 64, L[L_HEAD1].Wt, biasg, 512, 1, N, 0, y1))) return rc;
+  if ((rc = cg_linear_launch(ctx, y1, (int)P, 512, L[L_HEAD2].Wt, L[L_HEAD2].b, 256, 1, 0, 0, y2))) return rc;
+  if ((rc = cg_linear_launch(ctx, y2, (int)P, 256, L[L_HEAD3].Wt, L[L_HEAD3].b, 128, 1, 0, 0, y3))) return rc;
+  if ((rc = cg_linear_launch(ctx, y3, (int)P, 128, L[L_HEAD4].Wt, L[L_HEAD4].b, n_out, 0, 0, 0, lg))) return rc;
+  if (out_coords || out_conf || out_bins) {
+    CG_REQUIRE(ctx, bins > 0 && bins * 3 == n_out, "nunocs: n_out != 3*bins");
+    if ((rc = cg_nunocs_post_launch(ctx, lg, (int)P, bins, out_coords, out_conf, out_bins))) return rc;
+  }
+  return CG_OK;
+}
+
+}  // namespace
+
+extern "C" int cg_graspq_forward_dev(cg_net *net, const double *cloud_xyz, const double *cloud_nrm, int M,
+                                     const double *poses, int B, const int32_t *ids, int N, const double *mean,
+                                     const double *stdv, float *out_probs, int32_t *out_label) {
+  if (!net) return CG_EINVAL;
+  cg_ctx *ctx = net->ctx;
+  CG_REQUIRE(ctx, cloud_xyz && cloud_nrm && poses && M > 0, "graspq: null cloud/poses");
+  CG_REQUIRE(ctx, ids != nullptr || N <= M, "graspq: ids required when N > M");
+  CG_REQUIRE(ctx, (mean == nullptr) == (stdv == nullptr), "graspq: mean/std must come together");
+  cg_input_src in;
+  memset(&in, 0, sizeof(in));
+  in.cloud_xyz = cloud_xyz; in.cloud_nrm = cloud_nrm; in.poses = poses; in.ids = ids;
+  in.mean = mean; in.stdv = stdv; in.M = M;
+  return cls_forward_impl(net, in, B, N, nullptr, out_probs, out_label);
+}
+
+extern "C" int cg_graspq_forward_host(cg_net *net, const double *cloud_xyz, const double *cloud_nrm, int M,
+                                      const double *poses, int B, const int32_t *ids, int N, const double *mean,
+                                      const double *stdv, float *out_probs, int32_t *out_label) {
+  if (!net) return CG_EINVAL;
+  cg_ctx *ctx = net->ctx;
+  CG_REQUIRE(ctx, cloud_xyz && cloud_nrm && poses && ids && out_probs, "graspq_host: null argument");
+  CG_REQUIRE(ctx, M > 0 && B > 0 && N > 0, "graspq_host: bad shape");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int n_out = net->n_out;
+  const size_t need = cg_arena::pad((size_t)M * 3 * 8) * 2 + cg_arena::pad((size_t)B * 16 * 8) +
+                      cg_arena::pad((size_t)B * N * 4) + cg_arena::pad(6 * 8) * 2 +
+                      cg_arena::pad((size_t)B * n_out * 4) + cg_arena::pad((size_t)B * 4) + 4096;
+  int rc = cg_io_reserve(ctx, need);
+  if (rc) return rc;
+  cg_arena ar(ctx->io);
+  double *d_xyz = ar.take<double>((size_t)M * 3);
+  double *d_nrm = ar.take<double>((size_t)M * 3);
+  double *d_pose = ar.take<double>((size_t)B * 16);
+  int32_t *d_ids = ar.take<int32_t>((size_t)B * N);
+  double *d_mean = ar.take<double>(6);
+  double *d_std = ar.take<double>(6);
+  float *d_probs = ar.take<float>((size_t)B * n_out);
+  int32_t *d_label = ar.take<int32_t>(B);
+  cudaStream_t st = ctx->stream;
+  CG_CUDA(ctx, cudaMemcpyAsync(d_xyz, cloud_xyz, (size_t)M * 24, cudaMemcpyHostToDevice, st));
+  CG_CUDA(ctx, cudaMemcpyAsync(d_nrm, cloud_nrm, (size_t)M * 24, cudaMemcpyHostToDevice, st));
+  CG_CUDA(ctx, cudaMemcpyAsync(d_pose, poses, (size_t)B * 128, cudaMemcpyHostToDevice, st));
+  CG_CUDA(ctx, cudaMemcpyAsync(d_ids, ids, (size_t)B * N * 4, cudaMemcpyHostToDevice, st));
+  if (mean && stdv) {
+    CG_CUDA(ctx, cudaMemcpyAsync(d_mean, mean, 48, cudaMemcpyHostToDevice, st));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_std, stdv, 48, cudaMemcpyHostToDevice, st));
+  }
+  rc = cg_graspq_forward_dev(net, d_xyz, d_nrm, M, d_pose, B, d_ids, N, mean ? d_mean : nullptr,
+                             stdv ? d_std : nullptr, d_probs, d_label);
+  if (rc) return rc;
+  CG_CUDA(ctx, cudaMemcpyAsync(out_probs, d_probs, (size_t)B * n_out * 4, cudaMemcpyDeviceToHost, st));
+  if (out_label) CG_CUDA(ctx, cudaMemcpyAsync(out_label, d_label, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  CG_CUDA(ctx, cudaStreamSynchronize(st));
+  return CG_OK;
+}
+
+extern "C" int cg_cls_forward_dev(cg_net *net, const float *x, int B, int N, float *out_logits, float *out_probs) {
+  if (!net) return CG_EINVAL;
+  CG_REQUIRE(net->ctx, x != nullptr, "cls: null input");
+  cg_input_src in;
+  memset(&in, 0, sizeof(in));
+  in.x_direct = x;
+  return cls_forward_impl(net, in, B, N, out_logits, out_probs, nullptr);
+}
+
+extern "C" int cg_seg_forward_dev(cg_net *net, const float *x, int B, int N, float *out_logits) {
+  if (!net) return CG_EINVAL;
+  CG_REQUIRE(net->ctx, out_logits != nullptr, "seg: null output");
+  return seg_forward_impl(net, x, B, N, out_logits, 0, nullptr, nullptr, nullptr);
+}
+
+extern "C" int cg_nunocs_forward_dev(cg_net *net, const float *x, int N, int bins, float *out_coords,
+                                     float *out_conf_z, int32_t *out_bins) {
+  if (!net) return CG_EINVAL;
+  return seg_forward_impl(net, x, 1, N, nullptr, bins, out_coords, out_conf_z, out_bins);
+}
+
+extern "C" int cg_nunocs_forward_host(cg_net *net, const float *x_host, int N, int bins, float *out_coords,
+                                      float *out_conf_z, int32_t *out_bins) {
+  if (!net) return CG_EINVAL;
+  cg_ctx *ctx = net->ctx;
+  CG_REQUIRE(ctx, x_host && N > 0 && out_coords, "nunocs_host: bad arguments");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t need = cg_arena::pad((size_t)N * 24) + cg_arena::pad((size_t)N * 12) * 2 + cg_arena::pad((size_t)N * 4) + 4096;
+  int rc = cg_io_reserve(ctx, need);
+  if (rc) return rc;
+  cg_arena ar(ctx->io);
+  float *d_x = ar.take<float>((size_t)N * 6);
+  float *d_c = ar.take<float>((size_t)N * 3);
+  int32_t *d_b = ar.take<int32_t>((size_t)N * 3);
+  float *d_z = ar.take<float>(N);
+  cudaStream_t st = ctx->stream;
+  CG_CUDA(ctx, cudaMemcpyAsync(d_x, x_host, (size_t)N * 24, cudaMemcpyHostToDevice, st));
+  rc = cg_nunocs_forward_dev(net, d_x, N, bins, d_c, d_z, d_b);
+  if (rc) return rc;
+  CG_CUDA(ctx, cudaMemcpyAsync(out_coords, d_c, (size_t)N * 12, cudaMemcpyDeviceToHost, st));
+  if (out_conf_z) CG_CUDA(ctx, cudaMemcpyAsync(out_conf_z, d_z, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  if (out_bins) CG_CUDA(ctx, cudaMemcpyAsync(out_bins, d_b, (size_t)N * 12, cudaMemcpyDeviceToHost, st));
+  CG_CUDA(ctx, cudaStreamSynchronize(st));
+  return CG_OK;
+}

@@ -1,0 +1,145 @@
+"""Drop-in for the reference's pybind module ``my_cpp`` (my_cpp/pybind.cpp:11-23).
+
+``filterGraspPose`` keeps the reference's 20 positional arguments
+(my_cpp/common.h:60) and returns the surviving grasp_in_cam matrices as a list
+of (4,4) float32 arrays.  Differences, all documented in INTEGRATION.md:
+
+* geometry predicate = gripper SDF vs scene points (sdf.py:292-389) instead of
+  FCL mesh-vs-octree; the SDFs of the two gripper meshes must be registered
+  once with :func:`register_gripper_sdf` (the reference loads the same grids
+  from ``gripper*.sdf``, dexnet/grasping/gripper.py:120-129);
+* survivors come back in deterministic (pose, symmetry) order, not in OpenMP
+  thread-arrival order (common.cpp:303-313);
+* ``filter_ik=True`` needs a host IK predicate registered with
+  :func:`set_ik_solver` (the generated ikfast solver stays on the CPU).
+"""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_SDF_REGISTRY = {}
+_IK_SOLVER = None
+DEFAULT_SDF_MODE = _lib.CG_SDF_TRILINEAR
+
+
+def _digest(vertices, faces):
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(vertices, dtype=np.float32).tobytes())
+    h.update(np.ascontiguousarray(faces, dtype=np.int32).tobytes())
+    return h.hexdigest()
+
+
+def register_gripper_sdf(vertices, faces, sdf):
+    """Associate a gripper mesh (as passed to filterGraspPose) with its Sdf3D."""
+    _SDF_REGISTRY[_digest(vertices, faces)] = sdf
+
+
+def set_ik_solver(fn):
+    """fn(ee_in_base (4,4) float32, upper, lower) -> bool (True = some IK solution within limits)."""
+    global _IK_SOLVER
+    _IK_SOLVER = fn
+
+
+def _sdf_for(vertices, faces):
+    key = _digest(vertices, faces)
+    if key not in _SDF_REGISTRY:
+        raise _lib.CgError("no SDF registered for this gripper mesh: call "
+                           "catgrasp_b200.my_cpp.register_gripper_sdf(vertices, faces, Sdf3D) first")
+    return _SDF_REGISTRY[key]
+
+
+def _m16(m):
+    a = np.ascontiguousarray(np.asarray(m, dtype=np.float64).astype(np.float32)).reshape(16)
+    return (C.c_float * 16)(*[float(v) for v in a])
+
+
+def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_in_grasp,
+                          filter_approach_dir_face_camera, adjust_collision_pose, sdf_open, open_pts,
+                          sdf_enclosed, enclosed_pts, sdf_mode=None, device_out=False):
+    """Array-level entry: returns (status (Q,) u8, offset (Q,) i8, poses (Q,4,4) f32) with Q = G*S."""
+    ctx = sdf_open.ctx
+    prm = _lib.FilterParams()
+    prm.nocs_pose = _m16(nocs_pose)
+    prm.canonical_to_nocs = _m16(canonical_to_nocs)
+    prm.gripper_in_grasp = _m16(gripper_in_grasp)
+    prm.filter_approach_dir_face_camera = int(bool(filter_approach_dir_face_camera))
+    prm.adjust_collision_pose = int(bool(adjust_collision_pose))
+    prm.sdf_mode = DEFAULT_SDF_MODE if sdf_mode is None else int(sdf_mode)
+    if isinstance(grasp_poses, torch.Tensor) and grasp_poses.is_cuda:
+        dev = grasp_poses.device
+        gp = grasp_poses.to(torch.float32).contiguous().reshape(-1, 16)
+        st = torch.as_tensor(symmetry_tfs).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 16)
+        p1 = torch.as_tensor(open_pts).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 3)
+        p2 = torch.as_tensor(enclosed_pts).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 3)
+        G, S = gp.shape[0], st.shape[0]
+        Q = G * S
+        status = torch.empty((Q,), dtype=torch.uint8, device=dev)
+        offset = torch.empty((Q,), dtype=torch.int8, device=dev)
+        poses = torch.empty((Q, 4, 4), dtype=torch.float32, device=dev)
+        ctx.use_torch_stream()
+        ctx.check(ctx.lib.cg_filter_grasp_pose_dev(
+            ctx.h, C.byref(prm), _lib.ptr(gp), G, _lib.ptr(st), S, sdf_open.h, _lib.ptr(p1), p1.shape[0],
+            sdf_enclosed.h if sdf_enclosed is not None else None, _lib.ptr(p2), p2.shape[0],
+            _lib.ptr(status), _lib.ptr(offset), _lib.ptr(poses)))
+        return status, offset, poses
+    gp = np.ascontiguousarray(np.asarray(grasp_poses, dtype=np.float64).astype(np.float32)).reshape(-1, 16)
+    st = np.ascontiguousarray(np.asarray(symmetry_tfs, dtype=np.float64).astype(np.float32)).reshape(-1, 16)
+    p1 = np.ascontiguousarray(np.asarray(open_pts, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+    p2 = np.ascontiguousarray(np.asarray(enclosed_pts, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+    G, S = gp.shape[0], st.shape[0]
+    Q = G * S
+    status = np.empty((Q,), np.uint8)
+    offset = np.empty((Q,), np.int8)
+    poses = np.empty((Q, 4, 4), np.float32)
+    ctx.check(ctx.lib.cg_filter_grasp_pose_host(
+        ctx.h, C.byref(prm), _lib.ptr(gp), G, _lib.ptr(st), S, sdf_open.h, _lib.ptr(p1), p1.shape[0],
+        sdf_enclosed.h if sdf_enclosed is not None else None, _lib.ptr(p2), p2.shape[0],
+        _lib.ptr(status), _lib.ptr(offset), _lib.ptr(poses)))
+    return status, offset, poses
+
+
+def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform, cam_in_world, ee_in_grasp,
+                    gripper_in_grasp, filter_approach_dir_face_camera, filter_ik, adjust_collision_pose, upper, lower,
+                    gripper_vertices, gripper_faces, gripper_enclosed_vertices, gripper_enclosed_faces,
+                    gripper_collision_pts, gripper_enclosed_collision_pts, octo_resolution, verbose):
+    """my_cpp/common.cpp:156-321 (signature common.h:60).  Returns list[(4,4) float32]."""
+    if len(grasp_poses) == 0 or len(symmetry_tfs) == 0:
+        return []
+    for name, a in (("gripper_collision_pts", gripper_collision_pts),
+                    ("gripper_enclosed_collision_pts", gripper_enclosed_collision_pts)):
+        a = np.asarray(a)
+        if a.size and (a.ndim != 2 or a.shape[1] != 3):   # collision_manager.cpp:57-61 (reference exits)
+            raise ValueError(f"{name} must be (N,3), got {a.shape}")
+    sdf_open = _sdf_for(gripper_vertices, gripper_faces)
+    sdf_encl = _sdf_for(gripper_enclosed_vertices, gripper_enclosed_faces)
+    if filter_ik and _IK_SOLVER is None:
+        raise NotImplementedError("filter_ik=True requires catgrasp_b200.my_cpp.set_ik_solver(fn); "
+                                  "the generated ikfast solver is a host stage (INTEGRATION.md)")
+    status, offset, poses = filter_grasp_pose_raw(
+        grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform, gripper_in_grasp,
+        filter_approach_dir_face_camera, adjust_collision_pose, sdf_open,
+        np.asarray(gripper_collision_pts).reshape(-1, 3), sdf_encl,
+        np.asarray(gripper_enclosed_collision_pts).reshape(-1, 3))
+    keep = status == _lib.CG_ST_ACCEPT
+    n_ik = 0
+    if filter_ik:
+        # common.cpp:214-226: IK is evaluated on the UN-shifted grasp_in_cam; the approach / IK / collision
+        # tests are independent rejections, so running IK on the collision survivors keeps the same set.
+        S = len(symmetry_tfs)
+        cam = np.asarray(cam_in_world, np.float64).astype(np.float32)
+        eeg = np.asarray(ee_in_grasp, np.float64).astype(np.float32)
+        shifts = np.array([0.0, 0.001, -0.001, 0.002, -0.002], np.float32)
+        for q in np.nonzero(keep)[0]:
+            g = poses[q].copy()
+            g[:3, 3] -= shifts[offset[q]] * g[:3, 1]
+            if not _IK_SOLVER(cam @ g @ eeg, upper, lower):
+                keep[q] = False
+                n_ik += 1
+    if verbose:
+        print("n_approach_dir_rej={}, n_ik_rej={}, n_open_gripper_rej={}, n_close_gripper_rej={}".format(
+            int((status == _lib.CG_ST_REJ_DIR).sum()), n_ik, int((status == _lib.CG_ST_REJ_COLL).sum()), 0))
+    return [poses[q].copy() for q in np.nonzero(keep)[0]]

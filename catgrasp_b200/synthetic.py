@@ -1,0 +1,245 @@
+"""Seeded synthetic assets for tests and bench: the reference ships no weights,
+meshes, SDFs or datasets (README.md:68-75), so parity and throughput run on these.
+
+Everything here is numpy on the host and deterministic for a given seed.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+# ----------------------------------------------------------------------------- checkpoints
+_ENC_SHAPES = [
+    ("feat.stn.conv1", (64, 6, 1)), ("feat.stn.conv2", (128, 64, 1)), ("feat.stn.conv3", (1024, 128, 1)),
+    ("feat.stn.fc1", (512, 1024)), ("feat.stn.fc2", (256, 512)), ("feat.stn.fc3", (9, 256)),
+    ("feat.stn.bn1", 64), ("feat.stn.bn2", 128), ("feat.stn.bn3", 1024), ("feat.stn.bn4", 512), ("feat.stn.bn5", 256),
+    ("feat.conv1", (64, 6, 1)), ("feat.conv2", (128, 64, 1)), ("feat.conv3", (1024, 128, 1)),
+    ("feat.bn1", 64), ("feat.bn2", 128), ("feat.bn3", 1024),
+    ("feat.fstn.conv1", (64, 64, 1)), ("feat.fstn.conv2", (128, 64, 1)), ("feat.fstn.conv3", (1024, 128, 1)),
+    ("feat.fstn.fc1", (512, 1024)), ("feat.fstn.fc2", (256, 512)), ("feat.fstn.fc3", (4096, 256)),
+    ("feat.fstn.bn1", 64), ("feat.fstn.bn2", 128), ("feat.fstn.bn3", 1024), ("feat.fstn.bn4", 512),
+    ("feat.fstn.bn5", 256),
+]
+
+
+def _head_shapes(kind, n_out):
+    if kind == "cls":   # pointnet2.py:281-286
+        return [("fc1", (512, 1024)), ("fc2", (256, 512)), ("fc3", (n_out, 256)), ("bn1", 512), ("bn2", 256)]
+    return [("conv1", (512, 1088, 1)), ("conv2", (256, 512, 1)), ("conv3", (128, 256, 1)),   # pointnet2.py:308-314
+            ("conv4", (n_out, 128, 1)), ("bn1", 512), ("bn2", 256), ("bn3", 128)]
+
+
+def make_state_dict(kind, n_out, seed=0, module_prefix=True, as_torch=True):
+    """A PointNetCls ('cls') / PointNetSeg ('seg') state_dict with torch-default-like weight ranges
+    (U(+-1/sqrt(fan_in))) and randomised BatchNorm statistics so that folding is exercised:
+    running_mean ~ N(0,0.2), running_var ~ U(0.5,1.5), weight ~ U(0.5,1.5), bias ~ N(0,0.1)."""
+    rng = np.random.RandomState(seed)
+    sd = OrderedDict()
+    for name, shp in _ENC_SHAPES + _head_shapes(kind, n_out):
+        if isinstance(shp, tuple):
+            fan_in = shp[1]
+            bound = 1.0 / np.sqrt(fan_in)
+            sd[name + ".weight"] = rng.uniform(-bound, bound, size=shp).astype(np.float32)
+            sd[name + ".bias"] = rng.uniform(-bound, bound, size=(shp[0],)).astype(np.float32)
+        else:
+            sd[name + ".weight"] = rng.uniform(0.5, 1.5, size=(shp,)).astype(np.float32)
+            sd[name + ".bias"] = rng.normal(0, 0.1, size=(shp,)).astype(np.float32)
+            sd[name + ".running_mean"] = rng.normal(0, 0.2, size=(shp,)).astype(np.float32)
+            sd[name + ".running_var"] = rng.uniform(0.5, 1.5, size=(shp,)).astype(np.float32)
+            sd[name + ".num_batches_tracked"] = np.array(100, dtype=np.int64)
+    if as_torch:
+        import torch
+        sd = OrderedDict((k, torch.from_numpy(np.asarray(v))) for k, v in sd.items())
+    if module_prefix:   # checkpoints come from nn.DataParallel (trainer_grasp.py:33)
+        sd = OrderedDict(("module." + k, v) for k, v in sd.items())
+    return sd
+
+
+def write_artifacts(artifact_dir, kind, n_pts, seed=0, with_normalizer=True, ce_loss_bins=100):
+    """Create an artifacts directory in the reference's layout (predicter.py:41-64, :101-132)."""
+    import os
+    import pickle
+    import torch
+    import yaml
+    os.makedirs(artifact_dir, exist_ok=True)
+    if kind == "cls":
+        classes = [float(v) for v in np.linspace(0, 1, 11)]   # config_grasp.yml: 11 edges -> 10 classes
+        cfg = {"n_pts": int(n_pts), "input_channel": 6, "classes": classes, "batch_size": 240}
+        n_out = 10
+        cfg_name = "config_grasp.yml"
+    else:
+        cfg = {"n_pts": int(n_pts), "input_channel": 6, "ce_loss_bins": int(ce_loss_bins), "batch_size": 34}
+        n_out = 3 * int(ce_loss_bins)
+        cfg_name = "config_nunocs.yml"
+    with open(os.path.join(artifact_dir, cfg_name), "w") as f:
+        yaml.safe_dump(cfg, f)
+    sd = make_state_dict(kind, n_out, seed=seed)
+    torch.save({"epoch": 1, "state_dict": sd, "best_res": 0.0}, os.path.join(artifact_dir, "best_val.pth.tar"))
+    if with_normalizer:
+        rng = np.random.RandomState(seed + 7)
+        mean = np.concatenate([rng.normal(0, 0.002, 3), rng.normal(0, 0.05, 3)])
+        std = np.concatenate([rng.uniform(0.008, 0.012, 3), rng.uniform(0.5, 0.6, 3)])
+        with open(os.path.join(artifact_dir, "normalizer.pkl"), "wb") as f:
+            pickle.dump({"mean": mean, "std": std}, f)
+    return artifact_dir
+
+
+# ----------------------------------------------------------------------------- geometry
+def random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def sample_hex_nut(n, rng, across_flats=0.020, height=0.008, bore=0.010):
+    """Surface samples + outward normals of a hex nut (20 mm AF, 8 mm high, 10 mm bore)."""
+    R = across_flats / np.sqrt(3.0)            # circumradius
+    a_side = 6 * R * height
+    a_cap = 2 * (1.5 * np.sqrt(3) * R * R - np.pi * (bore / 2) ** 2)
+    a_bore = np.pi * bore * height
+    w = np.array([a_side, a_cap, a_bore])
+    which = rng.choice(3, size=n, p=w / w.sum())
+    pts = np.zeros((n, 3))
+    nrm = np.zeros((n, 3))
+    # sides
+    m = which == 0
+    k = rng.randint(0, 6, size=m.sum())
+    t = rng.uniform(0, 1, size=m.sum())
+    a0, a1 = k * np.pi / 3, (k + 1) * np.pi / 3
+    p0 = np.stack([R * np.cos(a0), R * np.sin(a0)], 1)
+    p1 = np.stack([R * np.cos(a1), R * np.sin(a1)], 1)
+    xy = p0 + (p1 - p0) * t[:, None]
+    am = (a0 + a1) / 2
+    pts[m] = np.concatenate([xy, rng.uniform(-height / 2, height / 2, size=(m.sum(), 1))], 1)
+    nrm[m] = np.stack([np.cos(am), np.sin(am), np.zeros_like(am)], 1)
+    # caps (rejection sample the hexagon minus the bore)
+    m = which == 1
+    cnt = m.sum()
+    xy = np.zeros((0, 2))
+    while xy.shape[0] < cnt:
+        c = rng.uniform(-R, R, size=(2 * cnt + 16, 2))
+        ang = np.arctan2(c[:, 1], c[:, 0]) % (np.pi / 3) - np.pi / 6
+        rad = np.linalg.norm(c, axis=1)
+        ok = (rad * np.cos(ang) <= across_flats / 2) & (rad >= bore / 2)
+        xy = np.concatenate([xy, c[ok]], 0)
+    xy = xy[:cnt]
+    s = rng.choice([-1.0, 1.0], size=cnt)
+    pts[m] = np.concatenate([xy, (s * height / 2)[:, None]], 1)
+    nrm[m] = np.stack([np.zeros(cnt), np.zeros(cnt), s], 1)
+    # bore
+    m = which == 2
+    th = rng.uniform(0, 2 * np.pi, size=m.sum())
+    pts[m] = np.stack([bore / 2 * np.cos(th), bore / 2 * np.sin(th), rng.uniform(-height / 2, height / 2, m.sum())], 1)
+    nrm[m] = np.stack([-np.cos(th), -np.sin(th), np.zeros_like(th)], 1)
+    return pts, nrm
+
+
+def make_pile(n_points, n_objects=24, seed=0, bin_size=0.10, floor_z=0.70):
+    """A clutter pile of hex nuts in the camera frame (z >= 0.1 as required by dataset_grasp.py:64).
+
+    Returns dict(cloud_xyz (n_points,3) f64, cloud_normal (n_points,3) f64, object_id (n_points,),
+    object_poses (n_objects,4,4)); only camera-facing samples are kept and normals point at the camera
+    (Utils.py:205-213)."""
+    rng = np.random.RandomState(seed)
+    per = int(np.ceil(n_points * 2.5 / n_objects))
+    P, Nn, ids, poses = [], [], [], []
+    for k in range(n_objects):
+        p, n = sample_hex_nut(per, rng)
+        Rm = random_rotation(rng)
+        t = np.array([rng.uniform(-bin_size / 2, bin_size / 2), rng.uniform(-bin_size / 2, bin_size / 2),
+                      floor_z - rng.uniform(0.004, 0.03)])
+        T = np.eye(4)
+        T[:3, :3] = Rm
+        T[:3, 3] = t
+        p = p @ Rm.T + t
+        n = n @ Rm.T
+        vis = np.einsum("ij,ij->i", n, p) < 0      # facing the camera at the origin
+        P.append(p[vis]); Nn.append(n[vis]); ids.append(np.full(vis.sum(), k)); poses.append(T)
+    P = np.concatenate(P); Nn = np.concatenate(Nn); ids = np.concatenate(ids)
+    assert P.shape[0] >= n_points, "increase oversampling"
+    sel = rng.choice(P.shape[0], size=n_points, replace=False)
+    return {"cloud_xyz": P[sel].astype(np.float64), "cloud_normal": Nn[sel].astype(np.float64),
+            "object_id": ids[sel], "object_poses": np.stack(poses)}
+
+
+def _rot_x(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+
+
+def make_candidates(cloud_xyz, cloud_normal, n_cand, seed=0, hand_depth=0.03, approach_step=0.002, init_bite=0.005):
+    """Grasp poses from the reference's cone parametrisation (grasp_sampler.py:269-289):
+    approach = -normal, cone directions within 60 deg, in-plane rotations 0..150 step 30 deg, depth steps."""
+    rng = np.random.RandomState(seed)
+    out = np.zeros((n_cand, 4, 4))
+    sel = rng.randint(0, cloud_xyz.shape[0], size=n_cand)
+    for i, s in enumerate(sel):
+        approach = -cloud_normal[s] / np.linalg.norm(cloud_normal[s])
+        tmp = rng.normal(size=3)
+        minor = tmp - approach * np.dot(tmp, approach)
+        minor /= np.linalg.norm(minor)
+        major = np.cross(minor, approach)
+        R0 = np.stack([approach, major, minor], 1)
+        # cone direction: rotate about a random in-plane axis by up to 60 deg
+        ang = rng.uniform(0, np.pi / 3)
+        phi = rng.uniform(0, 2 * np.pi)
+        axis = np.array([0, np.cos(phi), np.sin(phi)])
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        R_cone = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+        R = R0 @ R_cone @ _rot_x(np.deg2rad(30.0 * rng.randint(0, 6)))
+        d = approach_step * rng.randint(0, int(hand_depth / approach_step))
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = cloud_xyz[s] + (init_bite + d) * R[:, 0]
+        out[i] = T
+    return out
+
+
+# ----------------------------------------------------------------------------- gripper proxy
+def _box_sdf(p, lo, hi):
+    c = (lo + hi) / 2
+    h = (hi - lo) / 2
+    q = np.abs(p - c) - h
+    return np.linalg.norm(np.maximum(q, 0), axis=-1) + np.minimum(q.max(axis=-1), 0)
+
+
+def _box_mesh(lo, hi):
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    V = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0],
+                  [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], dtype=np.float64)
+    F = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4],
+                  [1, 2, 6], [1, 6, 5], [2, 3, 7], [2, 7, 6], [3, 0, 4], [3, 4, 7]], dtype=np.int32)
+    return V, F
+
+
+def make_gripper_proxy(res=0.001, pad_cells=5):
+    """Two-finger box gripper: palm 40x60x30 mm, fingers 45x8x20 mm, opening 50 mm.
+
+    Gripper frame: +x is the approach axis (fingers extend from x=0 to x=0.045), +y the closing axis.
+    Returns a dict with, for 'open' and 'enclosed': mesh (V,F), sdf grid (data[i][j][k] f32, origin, res),
+    and ``gripper_in_grasp`` (4,4): the grasp centre sits 10 mm behind the finger tips."""
+    palm = (np.array([-0.040, -0.030, -0.015]), np.array([0.0, 0.030, 0.015]))
+    f1 = (np.array([0.0, 0.025, -0.010]), np.array([0.045, 0.033, 0.010]))
+    f2 = (np.array([0.0, -0.033, -0.010]), np.array([0.045, -0.025, 0.010]))
+    gap = (np.array([0.0, -0.025, -0.010]), np.array([0.045, 0.025, 0.010]))
+    lo = np.array([-0.040, -0.033, -0.015]) - pad_cells * res
+    hi = np.array([0.045, 0.033, 0.015]) + pad_cells * res
+    dims = np.round((hi - lo) / res).astype(int) + 1
+    gi, gj, gk = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij")
+    P = lo[None, None, None, :] + res * np.stack([gi, gj, gk], -1)
+
+    def build(boxes):
+        sd = np.min(np.stack([_box_sdf(P, b[0], b[1]) for b in boxes], 0), 0)
+        Vs, Fs, off = [], [], 0
+        for b in boxes:
+            V, F = _box_mesh(b[0], b[1])
+            Vs.append(V); Fs.append(F + off); off += V.shape[0]
+        return {"V": np.concatenate(Vs), "F": np.concatenate(Fs).astype(np.int32),
+                "sdf": sd.astype(np.float32), "origin": lo.astype(np.float32), "res": np.float32(res)}
+
+    gig = np.eye(4)
+    gig[0, 3] = -0.035
+    return {"open": build([palm, f1, f2]), "enclosed": build([palm, f1, f2, gap]), "gripper_in_grasp": gig}

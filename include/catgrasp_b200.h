@@ -1,0 +1,206 @@
+/*
+ * catgrasp_b200.h -- C ABI of libcatgrasp_b200.so (sm_100a).
+ *
+ * This is the drop-in boundary for CaTGrasp's per-scene grasp-scoring hot
+ * path.  Every entry point is `extern "C"`, takes plain pointers and sizes,
+ * returns an int status (0 = ok, negative = CG_E*), and never calls exit().
+ * Each entry cites the reference interface (file:line under the reference
+ * checkout) that it replaces.
+ *
+ * Pointer conventions
+ *   *_host : the function takes HOST buffers, performs H2D, compute and D2H
+ *            itself on the context stream and returns after the result is in
+ *            the host output buffer (the reference-facing, blocking call).
+ *   *_dev  : all data pointers are DEVICE pointers owned by the caller
+ *            (e.g. torch allocations); the call enqueues work on the context
+ *            stream and returns without synchronising.
+ * Row-major everywhere.  Poses are 4x4 row-major.
+ */
+#ifndef CATGRASP_B200_H
+#define CATGRASP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+#define CG_OK            0
+#define CG_EINVAL       -1   /* bad argument / shape (reference: printf+exit(1),
+                                my_cpp/collision_manager.cpp:17-27,57-61)     */
+#define CG_ECUDA        -2   /* CUDA runtime error, see cg_last_error()       */
+#define CG_ENOMEM       -3
+#define CG_EUNSUPPORTED -4
+
+typedef struct cg_ctx cg_ctx;   /* one per device; owns stream + workspace    */
+typedef struct cg_net cg_net;   /* folded PointNetCls / PointNetSeg weights   */
+typedef struct cg_sdf cg_sdf;   /* one Sdf3D grid resident in HBM             */
+
+/* ---- context ----------------------------------------------------------- */
+int         cg_ctx_create(int device, cg_ctx **out);
+void        cg_ctx_destroy(cg_ctx *ctx);
+/* Use a caller-owned cudaStream_t (passed as void*); NULL = context's own. */
+int         cg_ctx_set_stream(cg_ctx *ctx, void *cuda_stream);
+int         cg_ctx_synchronize(cg_ctx *ctx);
+const char *cg_last_error(cg_ctx *ctx);
+const char *cg_version(void);
+/* number of kernels this library launched on ctx since creation / reset.   */
+int64_t     cg_ctx_launch_count(cg_ctx *ctx);
+void        cg_ctx_reset_launch_count(cg_ctx *ctx);
+/* GEMM engine for the 128->1024 shared-MLP layers:
+ *   0 = fp32 SIMT (exact-order reference engine), 1 = tcgen05 tensor cores.  */
+int         cg_ctx_set_engine(cg_ctx *ctx, int engine);
+int         cg_ctx_get_engine(cg_ctx *ctx);
+/* Optional in-stream timing of the dominant kernel (the fused shared-MLP+max
+ * "trunk"): when enabled every trunk launch is bracketed by a CUDA event pair
+ * on the launching stream; cg_ctx_profile_read() synchronises those events and
+ * returns the summed duration and the launch count, then clears the list.   */
+int         cg_ctx_profile(cg_ctx *ctx, int enable);
+int         cg_ctx_profile_read(cg_ctx *ctx, double *ms_total, int64_t *launches);
+
+/* ---- networks ----------------------------------------------------------
+ * Replaces: pointnet2.py:275-299 (PointNetCls), :302-329 (PointNetSeg),
+ * loaded through Utils.py:135-148 (load_model).  The host side folds every
+ * BatchNorm into the preceding conv/linear and packs fp32 weights in the
+ * order documented in catgrasp_b200/weights.py; `blob` is that packing.
+ *   kind: 0 = PointNetCls(n_in=6, n_out), 1 = PointNetSeg(n_in=6, n_out)     */
+#define CG_NET_CLS 0
+#define CG_NET_SEG 1
+int  cg_net_create(cg_ctx *ctx, int kind, int n_out,
+                   const float *blob_host, size_t blob_floats, cg_net **out);
+void cg_net_destroy(cg_net *net);
+size_t cg_net_blob_floats(int kind, int n_out);
+
+/* Grasp-Q forward over B candidates.
+ * Replaces: predicter.py:67-94 (GraspPredicter.predict_batch) incl. the
+ * per-candidate GraspDataset.transform (dataset_grasp.py:63-91) which is
+ * fused into the first kernel: for candidate b, point n
+ *     id   = ids[b*N+n]                       (host-drawn numpy RNG indices)
+ *     xyz  = inv(pose_b)     * cloud_xyz[id]  (float64, like the reference)
+ *     nrm  = inv(pose_b[:3,:3]) * cloud_nrm[id]
+ *     in6  = ([xyz,nrm] - mean) / (std + 1e-15)   (if mean/std != NULL)
+ * then PointNetCls forward + softmax in fp32.
+ *   cloud_xyz, cloud_nrm : (M,3) float64      poses : (B,4,4) float64
+ *   ids : (B,N) int32 in [0,M)                mean,std : (6,) float64 or NULL
+ *   out_probs : (B,n_out) float32             out_label : (B,) int32 or NULL
+ */
+int cg_graspq_forward_host(cg_net *net,
+                           const double *cloud_xyz, const double *cloud_nrm, int M,
+                           const double *poses, int B,
+                           const int32_t *ids, int N,
+                           const double *mean, const double *std,
+                           float *out_probs, int32_t *out_label);
+int cg_graspq_forward_dev(cg_net *net,
+                          const double *cloud_xyz, const double *cloud_nrm, int M,
+                          const double *poses, int B,
+                          const int32_t *ids, int N,
+                          const double *mean, const double *std,
+                          float *out_probs, int32_t *out_label);
+
+/* PointNetCls / PointNetSeg forward on an already materialised input tensor
+ * x : (B,N,6) float32 (device).  Replaces pointnet2.py:289-299 / :316-329.
+ *   cls: out_logits (B,n_out) and/or out_probs (B,n_out) (either may be NULL)
+ *   seg: out_logits (B,N,n_out) float32                                     */
+int cg_cls_forward_dev(cg_net *net, const float *x, int B, int N,
+                       float *out_logits, float *out_probs);
+int cg_seg_forward_dev(cg_net *net, const float *x, int B, int N,
+                       float *out_logits);
+/* NUNOCS post-processing, predicter.py:144-150: logits (P, 3*bins) ->
+ * coords (P,3) = argmax*(1/bins) - 0.5 and conf_z (P,) = softmax prob of the
+ * z-axis argmax bin.  Fused variant of cg_seg_forward for B=1.              */
+int cg_nunocs_forward_host(cg_net *net, const float *x_host, int N, int bins,
+                           float *out_coords, float *out_conf_z, int32_t *out_bins);
+int cg_nunocs_forward_dev(cg_net *net, const float *x, int N, int bins,
+                          float *out_coords, float *out_conf_z, int32_t *out_bins);
+
+/* ---- SDF grid ----------------------------------------------------------
+ * Replaces: meshpy/meshpy/sdf.py:217-289 (Sdf3D), sdf_file.py:59-87.
+ * grid is data[i][j][k] row-major (k fastest) float32; grid coordinate of a
+ * point x (SDF frame) is (x - origin) / resolution (sdf.py:252-264).        */
+int  cg_sdf_create(cg_ctx *ctx, const float *grid_host, int nx, int ny, int nz,
+                   const float origin[3], float resolution, cg_sdf **out);
+void cg_sdf_destroy(cg_sdf *sdf);
+/* Point-wise signed distance lookups at GRID coordinates (P,3) float32.
+ *   mode 0: trilinear, sdf.py:292-343 (_signed_distance)
+ *   mode 1: nearest cell with clamp, sdf.py:345-359 (_signed_distance_batch) */
+#define CG_SDF_TRILINEAR 0
+#define CG_SDF_NEAREST   1
+int cg_sdf_lookup_dev(cg_sdf *sdf, const float *grid_coords, int P, int mode,
+                      float *out_sd);
+
+/* ---- collision filter --------------------------------------------------
+ * Replaces: my_cpp/common.cpp:156-321 (filterGraspPose) with the FCL
+ * mesh-vs-octree test (collision_manager.cpp:93-111) substituted by the
+ * gripper-SDF predicate of sdf.py:377-389 (is_any_points_inside, nearest
+ * mode) or its trilinear form (sdf.py:292-343).  IK (common.cpp:214-226) is
+ * NOT evaluated here: pass filter results to the host
+ * ikfast stage.
+ *   grasp_poses (G,4,4), symmetry_tfs (S,4,4), the five 4x4 matrices:
+ *       float32 row-major (the reference narrows float64 -> float at the
+ *       pybind boundary, common.h:51,60).
+ *   open_pts (P1,3), enclosed_pts (P2,3): float32 camera-frame points
+ *       (gripper_collision_pts / gripper_enclosed_collision_pts).
+ *   Outputs are indexed by pair q = i*S + j, i.e. DETERMINISTIC order
+ *   (the reference's is thread-arrival order, common.cpp:303-313):
+ *   out_status[q] : 0 accepted, 1 rejected by approach direction,
+ *                   3 rejected by collision (2 is reserved for IK)
+ *   out_offset[q] : index 0..4 of the winning lateral offset
+ *                   (0,+1mm,-1mm,+2mm,-2mm; common.cpp:255-262), -1 if none
+ *   out_poses[q]  : (4,4) float32 grasp_in_cam shifted by the winning offset,
+ *                   all-zero when rejected (common.cpp:289-293)              */
+#define CG_ST_ACCEPT    0
+#define CG_ST_REJ_DIR   1
+#define CG_ST_REJ_IK    2
+#define CG_ST_REJ_COLL  3
+typedef struct cg_filter_params {
+  float nocs_pose[16];
+  float canonical_to_nocs[16];
+  float gripper_in_grasp[16];
+  int   filter_approach_dir_face_camera;
+  int   adjust_collision_pose;
+  int   sdf_mode;          /* CG_SDF_TRILINEAR or CG_SDF_NEAREST */
+} cg_filter_params;
+
+int cg_filter_grasp_pose_host(cg_ctx *ctx, const cg_filter_params *prm,
+                              const float *grasp_poses, int G,
+                              const float *symmetry_tfs, int S,
+                              cg_sdf *sdf_open, const float *open_pts, int P1,
+                              cg_sdf *sdf_enclosed, const float *enclosed_pts, int P2,
+                              uint8_t *out_status, int8_t *out_offset, float *out_poses);
+int cg_filter_grasp_pose_dev(cg_ctx *ctx, const cg_filter_params *prm,
+                             const float *grasp_poses, int G,
+                             const float *symmetry_tfs, int S,
+                             cg_sdf *sdf_open, const float *open_pts, int P1,
+                             cg_sdf *sdf_enclosed, const float *enclosed_pts, int P2,
+                             uint8_t *out_status, int8_t *out_offset, float *out_poses);
+
+/* ---- PointNet++ primitives (device pointers) ---------------------------
+ * Replace the free functions of pointnet2.py:14-149.  Indices are int32 on
+ * the device (the Python mirror widens to int64 like the reference).        */
+/* pointnet2.py:14-33  square_distance: (B,S,3),(B,N,3) -> (B,S,N)           */
+int cg_square_distance_dev(cg_ctx *ctx, const float *src, const float *dst,
+                           int B, int S, int N, float *out);
+/* pointnet2.py:35-51  index_points: points (B,N,C), idx (B,S) -> (B,S,C)    */
+int cg_index_points_dev(cg_ctx *ctx, const float *points, const int32_t *idx,
+                        int B, int N, int C, int S, float *out);
+/* pointnet2.py:54-75  farthest_point_sample with explicit start indices     */
+int cg_fps_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoint,
+               const int32_t *start_idx, int32_t *out_idx);
+/* pointnet2.py:78-98  query_ball_point (first nsample by index, pad w/ first;
+ * an empty ball yields N in every slot, like the reference).  radius2 is
+ * float32(radius**2), the threshold torch compares against (:93)            */
+int cg_ball_query_dev(cg_ctx *ctx, float radius2, int nsample,
+                      const float *xyz, const float *new_xyz,
+                      int B, int N, int S, int32_t *out_idx);
+/* pointnet2.py:101-129 grouping tail of sample_and_group:
+ * out (B,S,K,3+D) = [xyz[idx]-new_xyz, points[idx]]                         */
+int cg_group_points_dev(cg_ctx *ctx, const float *xyz, const float *points,
+                        const float *new_xyz, const int32_t *idx,
+                        int B, int N, int D, int S, int K, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATGRASP_B200_H */

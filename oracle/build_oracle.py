@@ -1,0 +1,23 @@
+"""Build recipe for the C part of the oracle (gcc only; no reference sources are compiled:
+my_cpp needs FCL + octomap + Boost which are neither vendored in /root/reference nor installed,
+so the reference's own collision code is UNBUILDABLE here -- see DESIGN.md)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT_DIR = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT_DIR, "libfilter_ref.so")
+
+
+def build(force=False):
+    src = os.path.join(HERE, "filter_ref.c")
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+        return LIB
+    os.makedirs(OUT_DIR, exist_ok=True)
+    cmd = ["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", LIB, src, "-lm"]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True))

@@ -1,0 +1,181 @@
+"""CPU tests: the C ABI library loads and exports every symbol of include/*.h, host logic,
+weight folding, and that the product path fails loudly without a GPU / without the extension."""
+import copy
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from catgrasp_b200 import _lib
+from catgrasp_b200.synthetic import make_gripper_proxy, make_pile, make_candidates, make_state_dict
+from catgrasp_b200.weights import BLOB_ORDER, pack_blob, strip_module_prefix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "catgrasp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from catgrasp_b200 import build
+    build.build()
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/catgrasp_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes prototype"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert b"sm_100a" in lib.cg_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.CgError):
+        _lib.Context(0)
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libcatgrasp_b200.so")
+    with pytest.raises(_lib.CgError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "catgrasp_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "oracle/" not in txt or f == "cg_collide.cu"   # cg_collide.cu only names the oracle file in a comment
+
+
+@pytest.mark.parametrize("kind,n_out", [("cls", 10), ("seg", 300)])
+def test_blob_size_matches_library(kind, n_out):
+    lib = _lib.load()
+    blob, n = pack_blob(make_state_dict(kind, n_out, seed=3), kind)
+    assert n == n_out and blob.dtype == np.float32
+    assert blob.size == lib.cg_net_blob_floats(0 if kind == "cls" else 1, n_out)
+    assert len(BLOB_ORDER) == 20
+
+
+def test_bn_folding_matches_conv_bn():
+    """Folded (Wt, b) reproduce conv1d + eval BatchNorm (pointnet2.py:171) to fp32 round-off."""
+    import torch.nn.functional as F
+    from catgrasp_b200.weights import _fold
+    sd = strip_module_prefix(make_state_dict("cls", 10, seed=5))
+    x = torch.randn(2, 64, 50)
+    y = F.conv1d(x, sd["feat.stn.conv2.weight"], sd["feat.stn.conv2.bias"])
+    y = F.batch_norm(y, sd["feat.stn.bn2.running_mean"], sd["feat.stn.bn2.running_var"], sd["feat.stn.bn2.weight"],
+                     sd["feat.stn.bn2.bias"], training=False, eps=1e-5)
+    Wt, b = _fold(sd, "feat.stn.conv2", "feat.stn.bn2")
+    y2 = torch.einsum("bkn,kc->bcn", x.double(), torch.from_numpy(Wt)) + torch.from_numpy(b)[None, :, None]
+    assert (y.double() - y2).abs().max() < 1e-5
+
+
+def test_checkpoint_key_check():
+    sd = strip_module_prefix(make_state_dict("cls", 10, seed=0))
+    bad = copy.copy(sd)
+    bad.pop("fc3.bias")
+    with pytest.raises(RuntimeError):
+        pack_blob(bad, "cls")
+    with pytest.raises(RuntimeError):
+        pack_blob(sd, "seg")
+
+
+def test_host_id_draw_consumes_rng_like_reference():
+    """draw_subsample_ids == the ids GraspDataset.transform draws (dataset_grasp.py:72-73), candidate by candidate."""
+    from catgrasp_b200.predicter import draw_subsample_ids
+    from oracle.transforms_ref import grasp_transform
+    scene = make_pile(700, n_objects=2, seed=1)
+    data = {"cloud_xyz": scene["cloud_xyz"], "cloud_normal": scene["cloud_normal"]}
+    for n_pts in (256, 700, 1024):
+        np.random.seed(9)
+        ref = [grasp_transform(copy.deepcopy(data), np.eye(4), {"n_pts": n_pts})["ids"] for _ in range(3)]
+        after_ref = np.random.rand()
+        np.random.seed(9)
+        ids = draw_subsample_ids(700, n_pts, count=3)
+        assert np.random.rand() == after_ref
+        assert np.array_equal(ids, np.stack(ref))
+
+
+def test_sdf_file_layout_roundtrip(tmp_path):
+    """sdf_file.py:76-84: values are stored i fastest, k slowest and land in data[i][j][k]."""
+    from catgrasp_b200.sdf import parse_sdf_file, write_sdf_file
+    rng = np.random.RandomState(0)
+    data = rng.normal(size=(4, 5, 6)).astype(np.float32)
+    p = str(tmp_path / "g.sdf")
+    write_sdf_file(p, data, [0.1, 0.2, 0.3], 0.001)
+    d2, origin, res = parse_sdf_file(p)
+    assert np.allclose(d2, data, atol=1e-6) and np.allclose(origin, [0.1, 0.2, 0.3]) and res == 0.001
+    lines = open(p).read().split("\n")
+    assert float(lines[3]) == pytest.approx(float(data[0, 0, 0]), abs=1e-6)
+    assert float(lines[4]) == pytest.approx(float(data[1, 0, 0]), abs=1e-6)      # i is the fastest index
+
+
+def _mm4(A, B):
+    O = np.zeros((4, 4), np.float32)
+    for r in range(4):
+        for c in range(4):
+            s = np.float32(A[r, 0] * B[0, c])
+            for k in (1, 2, 3):
+                s = np.float32(s + np.float32(A[r, k] * B[k, c]))
+            O[r, c] = s
+    return O
+
+
+def test_filter_oracle_pose_logic_matches_eigen_order():
+    """oracle/filter_ref.c pose arithmetic == an independent numpy fp32 restatement of
+    common.cpp:159,190-197,265 (sequential fp32 products, normalise by division, float step values)."""
+    from oracle import filter_ref
+    rng = np.random.RandomState(0)
+    scene = make_pile(400, n_objects=2, seed=2)
+    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], 16, seed=3)
+    g = make_gripper_proxy()
+    far = scene["cloud_xyz"][:50] + 10.0                       # nothing collides: offset 0 must win
+    nocs = np.eye(4); nocs[:3, :3] *= np.array([1.0, 1.2, 0.8]); nocs[:3, 3] = [0.01, -0.02, 0.03]
+    c2n = np.eye(4); c2n[:3, 3] = rng.normal(0, 0.01, 3)
+    sym = np.eye(4); sym[:3, :3] = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1]])
+    st, off, out = filter_ref.filter_ref(poses, [sym], nocs, c2n, g["gripper_in_grasp"], False, True, 0, g["open"], far,
+                                         g["enclosed"], far)
+    assert (st == 0).all() and (off == 0).all()
+    f = lambda m: np.asarray(m, np.float64).astype(np.float32)
+    c2c = _mm4(f(nocs), f(c2n))
+    for i in range(len(poses)):
+        G = _mm4(c2c, _mm4(f(sym), f(poses[i])))
+        for col in range(3):
+            x, y, z = G[0, col], G[1, col], G[2, col]
+            n = np.sqrt(np.float32(np.float32(np.float32(x * x) + np.float32(y * y)) + np.float32(z * z)))
+            G[:3, col] = np.array([x / n, y / n, z / n], np.float32)
+        assert np.array_equal(G.view(np.uint32), out[i].view(np.uint32))
+    # everything collides -> zero matrices, offset -1, status 3 (common.cpp:289-293)
+    inside = (np.linalg.inv(np.eye(4)) @ np.eye(4))[:3, 3][None] + poses[0][:3, 3][None] - 0.035 * poses[0][:3, 0][None]
+    st, off, out = filter_ref.filter_ref(poses[:1], [np.eye(4)], np.eye(4), np.eye(4), g["gripper_in_grasp"], False, True,
+                                         0, g["open"], np.repeat(inside, 4, 0) - 0.02 * poses[0][:3, 0][None], None,
+                                         np.zeros((0, 3)))
+    assert st[0] == 3 and off[0] == -1 and (out == 0).all()
+    # the float accumulator of common.cpp:255
+    s1 = np.float32(0.001); s2 = np.float32(s1 + np.float32(0.001)); s3 = np.float32(s2 + np.float32(0.001))
+    assert float(s1) == 0.0010000000474974513 and float(s2) == 0.0020000000949949026 and not (float(s3) <= 0.003)
+
+
+def test_sdf_oracle_fp32_vs_reference_formula():
+    """C fp32 trilinear / nearest lookups agree with the float64 restatement of sdf.py:292-359."""
+    from oracle import filter_ref, sdf_ref
+    g = make_gripper_proxy()["open"]
+    rng = np.random.RandomState(1)
+    dims = np.array(g["sdf"].shape)
+    gc = rng.uniform(-3, dims.max() + 3, (4000, 3)).astype(np.float32)
+    tri = filter_ref.sdf_lookup_ref(g["sdf"], gc, 0)
+    assert np.abs(tri - sdf_ref.signed_distance(g["sdf"], gc.T)).max() < 1e-6
+    near = filter_ref.sdf_lookup_ref(g["sdf"], gc, 1)
+    assert np.array_equal(near, sdf_ref.signed_distance_nearest(g["sdf"], gc.T).astype(np.float32))

