@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- candidate grasps scored / second on the K2 workload (BASELINE.json configs[1]):
+a 20k-point nut pile, 4096 candidates per GPU, each candidate = one grasp-Q PointNet forward on a
+1024-point subset (fused per-candidate transform + softmax) AND one collision verdict (pose logic +
+gripper-SDF predicate over object/background points); one NUNOCS forward (8192 points) per step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n-pts 1024]
+
+N > 1 is launched by torchrun (one rank per GPU): candidates shard across ranks ("weak": 4096 per GPU),
+no data-path collective, one NCCL all-gather of the 48-byte result records per step.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_CAND = {1024: 880045568, 2048: 1754052096}     # SURVEY.md 8(d), exact from layer hooks on the reference
+# MACs per point of the three fused trunk kernels (conv chains incl. the 128->1024 layer; bmm / FC / 6->64 excluded
+# from nothing: 6*64 + [64*64] + 64*128 + 128*1024), SURVEY.md 8a N3-N5
+TRUNK_MAC_PER_PT = [6 * 64 + 64 * 128 + 128 * 1024,            # STN3d trunk
+                    6 * 64 + 64 * 64 + 64 * 128 + 128 * 1024,  # conv1 + STNkd trunk
+                    6 * 64 + 64 * 64 + 64 * 128 + 128 * 1024]  # conv1 + @T64 + conv2 + conv3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-pts", type=int, default=1024, help="points per candidate (config_grasp.yml n_pts)")
+    ap.add_argument("--candidates", type=int, default=4096, help="candidates per GPU")
+    ap.add_argument("--scene-pts", type=int, default=20000)
+    ap.add_argument("--nunocs-pts", type=int, default=8192)
+    ap.add_argument("--engine", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 (default: library default)")
+    ap.add_argument("--cpu-sample", type=int, default=192, help="candidates in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(args, rank):
+    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile
+    scene = make_pile(args.scene_pts, seed=0)
+    obj = scene["object_id"] == 3                      # the object being grasped
+    poses = make_candidates(scene["cloud_xyz"][obj], scene["cloud_normal"][obj], args.candidates, seed=1 + rank)
+    rng = np.random.RandomState(100 + rank)
+    M = args.scene_pts
+    # per-candidate subsets, drawn like dataset_grasp.py:72-73 (without replacement since M >= n_pts)
+    ids = np.stack([rng.permutation(M)[: args.n_pts] for _ in range(args.candidates)]).astype(np.int32)
+    norm = np.random.RandomState(7)
+    mean = np.concatenate([norm.normal(0, 0.002, 3), norm.normal(0, 0.05, 3)])
+    std = np.concatenate([norm.uniform(0.008, 0.012, 3), norm.uniform(0.5, 0.6, 3)])
+    # NUNOCS input of the target object (8192 draws with replacement from the object crop, min/max normalised)
+    oxyz, onrm = scene["cloud_xyz"][obj], scene["cloud_normal"][obj]
+    sel = rng.randint(0, oxyz.shape[0], size=args.nunocs_pts)
+    x = oxyz[sel]
+    x = (x - x.min(0)) / ((x.max(0) - x.min(0)).max() + 1e-15)
+    nun_in = np.concatenate([x, onrm[sel]], -1).astype(np.float32)
+    return {"scene": scene, "obj": obj, "poses": poses, "ids": ids, "mean": mean, "std": std, "nun_in": nun_in,
+            "open_pts": oxyz.astype(np.float32), "bg_pts": scene["cloud_xyz"][~obj].astype(np.float32),
+            "gripper": make_gripper_proxy()}
+
+
+def cpu_reference_pass(wl, args, n_cand, sd_cls, sd_seg, with_nunocs=True):
+    """The reference's CPU path for n_cand candidates: per-candidate numpy transform loop + PointNetCls in
+    micro-batches of 200 (predicter.py:67-94), C collision oracle with OpenMP on all cores, one NUNOCS forward."""
+    import torch
+    from oracle import filter_ref
+    from oracle.transforms_ref import nunocs_predict, predict_batch
+    scene = wl["scene"]
+    data = {"cloud_xyz": scene["cloud_xyz"], "cloud_normal": scene["cloud_normal"]}
+    cfg = {"n_pts": args.n_pts, "mean": wl["mean"], "std": wl["std"]}
+    t0 = time.perf_counter()
+    predict_batch(sd_cls, cfg, data, wl["poses"][:n_cand])
+    t1 = time.perf_counter()
+    g = wl["gripper"]
+    eye = np.eye(4)
+    filter_ref.filter_ref(wl["poses"][:n_cand], [eye], eye, eye, g["gripper_in_grasp"], True, True, 0, g["open"],
+                          wl["open_pts"], g["enclosed"], wl["bg_pts"], nthreads=os.cpu_count())
+    t2 = time.perf_counter()
+    if with_nunocs:
+        ncfg = {"n_pts": args.nunocs_pts, "ce_loss_bins": 100}
+        o = wl["obj"]
+        nunocs_predict(sd_seg, ncfg, {"cloud_xyz": scene["cloud_xyz"][o], "cloud_normal": scene["cloud_normal"][o]})
+    t3 = time.perf_counter()
+    return {"net_s": t1 - t0, "collision_s": t2 - t1, "nunocs_s": t3 - t2, "total_s": t3 - t0}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference's own
+    pointnet2.py / my_cpp cannot travel to / be built on the GPU box), each step a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    from catgrasp_b200.synthetic import make_state_dict
+    wl = make_workload(args, 0)
+    sd_cls, sd_seg = make_state_dict("cls", 10, seed=0), make_state_dict("seg", 300, seed=1)
+    n = min(args.cpu_sample, args.candidates)
+    n = max(8, n // 4)       # bounded: each step scores n candidates (+ one NUNOCS forward amortised like ours)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_pass(wl, args, n, sd_cls, sd_seg)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(wl, args, n, sd_cls, sd_seg)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    sample = f"{n} of {args.candidates} candidates per step (+1 NUNOCS forward), {args.scene_pts}-pt scene"
+    line = {"impl": "reference", "metric": "candidate grasps scored/sec", "value": v, "unit": "candidates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"K2 nut clutter pile: {args.scene_pts}-pt scene, {args.candidates} candidates/GPU, "
+                        f"n_pts={args.n_pts} per candidate, grasp-Q PointNetCls + SDF collision (5 lateral offsets, "
+                        f"trilinear) + 1 NUNOCS PointNetSeg forward ({args.nunocs_pts} pts) per step",
+            "candidates_per_gpu": args.candidates, "scene_pts": args.scene_pts, "n_pts": args.n_pts,
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"candidate-shard x{args.gpus}"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+
+    from catgrasp_b200 import _lib, my_cpp
+    from catgrasp_b200.dist import all_gather_records, pack_records
+    from catgrasp_b200.net import PointNetCls, PointNetSeg
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_state_dict
+
+    wl = make_workload(args, rank)
+    sd_cls, sd_seg = make_state_dict("cls", 10, seed=0), make_state_dict("seg", 300, seed=1)
+    cls = PointNetCls(sd_cls, device=local)
+    seg = PointNetSeg(sd_seg, device=local)
+    ctx = cls.ctx
+    if args.engine is not None:
+        ctx.set_engine(args.engine)
+    g = wl["gripper"]
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"], device=local)
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"], device=local)
+    B, N, M = args.candidates, args.n_pts, args.scene_pts
+    scene = wl["scene"]
+
+    # ---------------- device-resident inputs (the `value` leg)
+    d_xyz = torch.from_numpy(scene["cloud_xyz"]).to(dev)
+    d_nrm = torch.from_numpy(scene["cloud_normal"]).to(dev)
+    d_pose = torch.from_numpy(wl["poses"]).to(dev)
+    d_pose32 = d_pose.to(torch.float32).contiguous()
+    d_ids = torch.from_numpy(wl["ids"]).to(dev)
+    d_mean = torch.from_numpy(wl["mean"]).to(dev)
+    d_std = torch.from_numpy(wl["std"]).to(dev)
+    d_nun = torch.from_numpy(wl["nun_in"]).to(dev)
+    d_open = torch.from_numpy(wl["open_pts"]).to(dev)
+    d_bg = torch.from_numpy(wl["bg_pts"]).to(dev)
+    eye = np.eye(4)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        coords, conf, _ = seg.nunocs_dev(d_nun, 100)
+        probs, label = cls.graspq_dev(d_xyz, d_nrm, d_pose, d_ids, d_mean, d_std)
+        st, off, poses = my_cpp.filter_grasp_pose_raw(d_pose32, eye[None], eye, eye, g["gripper_in_grasp"], True, True,
+                                                      so, d_open, se, d_bg)
+        rec = pack_records(probs, st, off)
+        if world > 1:
+            rec = all_gather_records(rec, B * world)     # every rank holds a full block: one ncclAllGather
+        return rec, coords
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.reset_launch_count()
+    ctx.profile(True)
+    ctx.profile_read()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        flush.fill_(1)                      # evict L2 between timed iterations
+        rec, coords = step_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count()
+    trunk_ms, trunk_n = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+    checksum = float(rec[:, :10].sum().item())
+
+    # ---------------- e2e leg: reference-facing C-ABI calls on pinned HOST buffers, H2D + D2H inside the timed region
+    h = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in {
+        "xyz": scene["cloud_xyz"], "nrm": scene["cloud_normal"], "pose": wl["poses"], "ids": wl["ids"],
+        "mean": wl["mean"], "std": wl["std"], "nun": wl["nun_in"], "pose32": wl["poses"].astype(np.float32),
+        "open": wl["open_pts"], "bg": wl["bg_pts"]}.items()}
+    o_probs = torch.empty((B, 10), dtype=torch.float32).pin_memory()
+    o_label = torch.empty((B,), dtype=torch.int32).pin_memory()
+    o_coords = torch.empty((args.nunocs_pts, 3), dtype=torch.float32).pin_memory()
+    o_conf = torch.empty((args.nunocs_pts,), dtype=torch.float32).pin_memory()
+    o_bins = torch.empty((args.nunocs_pts, 3), dtype=torch.int32).pin_memory()
+    o_st = torch.empty((B,), dtype=torch.uint8).pin_memory()
+    o_off = torch.empty((B,), dtype=torch.int8).pin_memory()
+    o_poses = torch.empty((B, 4, 4), dtype=torch.float32).pin_memory()
+    import ctypes as C
+    prm = _lib.FilterParams()
+    for name, m in (("nocs_pose", eye), ("canonical_to_nocs", eye), ("gripper_in_grasp", g["gripper_in_grasp"])):
+        setattr(prm, name, (C.c_float * 16)(*[float(v) for v in np.asarray(m, np.float32).reshape(16)]))
+    prm.filter_approach_dir_face_camera, prm.adjust_collision_pose, prm.sdf_mode = 1, 1, 0
+    sym = torch.from_numpy(np.eye(4, dtype=np.float32)).pin_memory()
+    lib = ctx.lib
+    P = _lib.ptr
+
+    def step_host():
+        ctx.check(lib.cg_nunocs_forward_host(seg.h, P(h["nun"]), args.nunocs_pts, 100, P(o_coords), P(o_conf), P(o_bins)))
+        ctx.check(lib.cg_graspq_forward_host(cls.h, P(h["xyz"]), P(h["nrm"]), M, P(h["pose"]), B, P(h["ids"]), N,
+                                             P(h["mean"]), P(h["std"]), P(o_probs), P(o_label)))
+        ctx.check(lib.cg_filter_grasp_pose_host(ctx.h, C.byref(prm), P(h["pose32"]), B, P(sym), 1, so.h, P(h["open"]),
+                                                h["open"].shape[0], se.h, P(h["bg"]), h["bg"].shape[0], P(o_st),
+                                                P(o_off), P(o_poses)))
+
+    h2d = sum(h[k].numel() * h[k].element_size() for k in ("xyz", "nrm", "pose", "ids", "mean", "std", "nun", "pose32",
+                                                           "open", "bg")) + 64
+    d2h = sum(t_.numel() * t_.element_size() for t_ in (o_probs, o_label, o_coords, o_conf, o_bins, o_st, o_off, o_poses))
+    for _ in range(2):
+        step_host()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * e2e_steps / float(t.item())
+    agree = float(np.abs(o_probs.numpy() - rec[rank * B:(rank + 1) * B, :10].cpu().numpy()).max())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (fused shared-MLP + max "trunk")
+    peaks = load_peaks()
+    trunk_flops_per_step = 2.0 * sum(TRUNK_MAC_PER_PT) * (B * N + args.nunocs_pts)   # cls trunks + NUNOCS trunks
+    per_launch_ms = trunk_ms / max(trunk_n, 1)
+    flops_per_launch = trunk_flops_per_step * args.steps / max(trunk_n, 1)
+    achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "trunk (fused shared-MLP 6-64-[64]-128-1024 + max)",
+                "engine": ["fp32-simt", "tcgen05"][ctx.get_engine()],
+                "launches_timed": int(trunk_n), "avg_launch_ms": per_launch_ms,
+                "share_of_step": trunk_ms / ms, "peak_source": f"{peaks['source']} bf16 dense, sustained",
+                "frac_of_burst_peak": achieved / peaks["bf16_tflops"]}
+
+    line = {"metric": "candidate grasps scored/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "max_abs_dprob_vs_device_leg": agree},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "flop_per_candidate": FLOP_PER_CAND.get(N), "checksum": checksum}
+
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        n = min(args.cpu_sample, B)
+        r = cpu_reference_pass(wl, args, n, sd_cls, sd_seg)
+        line["cpu_baseline"] = {"value": n / r["total_s"], "unit": "candidates/s", "cores": os.cpu_count(),
+                                "kind": "port", "sample": f"{n} of {B} candidates + 1 NUNOCS forward "
+                                f"(net {r['net_s']:.2f}s, collision {r['collision_s']:.2f}s, nunocs {r['nunocs_s']:.2f}s)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,7 @@ SIGNATURES = {
     "cg_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "cg_ctx_destroy": (None, [_vp]),
     "cg_ctx_set_stream": (_i, [_vp, _vp]),
+    "cg_ctx_use_own_stream": (_i, [_vp]),
     "cg_ctx_synchronize": (_i, [_vp]),
     "cg_last_error": (C.c_char_p, [_vp]),
     "cg_version": (C.c_char_p, []),

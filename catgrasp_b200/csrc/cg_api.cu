@@ -41,7 +41,14 @@ extern "C" void cg_ctx_destroy(cg_ctx *ctx) {
 
 extern "C" int cg_ctx_set_stream(cg_ctx *ctx, void *cuda_stream) {
   if (!ctx) return CG_EINVAL;
-  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  // NULL is a real stream: the CUDA legacy default stream (what torch uses unless told otherwise)
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  return CG_OK;
+}
+
+extern "C" int cg_ctx_use_own_stream(cg_ctx *ctx) {
+  if (!ctx) return CG_EINVAL;
+  ctx->stream = ctx->own_stream;
   return CG_OK;
 }
 

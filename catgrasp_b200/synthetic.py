@@ -76,8 +76,12 @@ def write_artifacts(artifact_dir, kind, n_pts, seed=0, with_normalizer=True, ce_
     torch.save({"epoch": 1, "state_dict": sd, "best_res": 0.0}, os.path.join(artifact_dir, "best_val.pth.tar"))
     if with_normalizer:
         rng = np.random.RandomState(seed + 7)
-        mean = np.concatenate([rng.normal(0, 0.002, 3), rng.normal(0, 0.05, 3)])
-        std = np.concatenate([rng.uniform(0.008, 0.012, 3), rng.uniform(0.5, 0.6, 3)])
+        if kind == "cls":   # grasp-frame coordinates in metres (dataset_grasp.py:84-85)
+            mean = np.concatenate([rng.normal(0, 0.002, 3), rng.normal(0, 0.05, 3)])
+            std = np.concatenate([rng.uniform(0.008, 0.012, 3), rng.uniform(0.5, 0.6, 3)])
+        else:               # min/max-normalised coordinates in [0,1] (augmentations.py:70-75)
+            mean = np.concatenate([rng.normal(0.5, 0.05, 3), rng.normal(0, 0.05, 3)])
+            std = np.concatenate([rng.uniform(0.25, 0.35, 3), rng.uniform(0.5, 0.6, 3)])
         with open(os.path.join(artifact_dir, "normalizer.pkl"), "wb") as f:
             pickle.dump({"mean": mean, "std": std}, f)
     return artifact_dir
@@ -136,20 +140,36 @@ def sample_hex_nut(n, rng, across_flats=0.020, height=0.008, bore=0.010):
     return pts, nrm
 
 
-def make_pile(n_points, n_objects=24, seed=0, bin_size=0.10, floor_z=0.70):
+def make_pile(n_points, n_objects=8, seed=0, bin_size=0.10, floor_z=0.70, max_tilt_deg=30.0):
     """A clutter pile of hex nuts in the camera frame (z >= 0.1 as required by dataset_grasp.py:64).
 
-    Returns dict(cloud_xyz (n_points,3) f64, cloud_normal (n_points,3) f64, object_id (n_points,),
-    object_poses (n_objects,4,4)); only camera-facing samples are kept and normals point at the camera
-    (Utils.py:205-213)."""
+    Nuts lie roughly flat (tilt <= max_tilt_deg, random yaw) at rejection-sampled, mostly non-overlapping
+    positions in a bin_size x bin_size bin whose floor is at camera z = floor_z; a second layer forms when
+    the bin is full.  Returns dict(cloud_xyz (n_points,3) f64, cloud_normal (n_points,3) f64,
+    object_id (n_points,), object_poses (n_objects,4,4)); only camera-facing samples are kept and normals
+    point at the camera (Utils.py:205-213)."""
     rng = np.random.RandomState(seed)
-    per = int(np.ceil(n_points * 2.5 / n_objects))
-    P, Nn, ids, poses = [], [], [], []
+    per = int(np.ceil(n_points * 2.6 / n_objects))
+    P, Nn, ids, poses, centers = [], [], [], [], []
     for k in range(n_objects):
         p, n = sample_hex_nut(per, rng)
-        Rm = random_rotation(rng)
-        t = np.array([rng.uniform(-bin_size / 2, bin_size / 2), rng.uniform(-bin_size / 2, bin_size / 2),
-                      floor_z - rng.uniform(0.004, 0.03)])
+        tilt = np.deg2rad(rng.uniform(0, max_tilt_deg))
+        phi = rng.uniform(0, 2 * np.pi)
+        axis = np.array([np.cos(phi), np.sin(phi), 0.0])
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        Rt = np.eye(3) + np.sin(tilt) * K + (1 - np.cos(tilt)) * (K @ K)
+        yaw = rng.uniform(0, 2 * np.pi)
+        Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+        Rm = Rt @ Rz
+        layer = 0
+        for attempt in range(200):
+            c = rng.uniform(-bin_size / 2 + 0.012, bin_size / 2 - 0.012, size=2)
+            if all(np.linalg.norm(c - q[:2]) > 0.025 or q[2] != layer for q in centers):
+                break
+            if attempt % 50 == 49:
+                layer += 1
+        centers.append(np.array([c[0], c[1], layer]))
+        t = np.array([c[0], c[1], floor_z - 0.006 - 0.009 * layer - rng.uniform(0, 0.002)])
         T = np.eye(4)
         T[:3, :3] = Rm
         T[:3, 3] = t
@@ -169,9 +189,10 @@ def _rot_x(a):
     return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
 
 
-def make_candidates(cloud_xyz, cloud_normal, n_cand, seed=0, hand_depth=0.03, approach_step=0.002, init_bite=0.005):
+def make_candidates(cloud_xyz, cloud_normal, n_cand, seed=0, hand_depth=0.012, approach_step=0.002, init_bite=0.002,
+                    cone_deg=35.0):
     """Grasp poses from the reference's cone parametrisation (grasp_sampler.py:269-289):
-    approach = -normal, cone directions within 60 deg, in-plane rotations 0..150 step 30 deg, depth steps."""
+    approach = -normal, cone directions within ``cone_deg`` (reference: 60 deg), in-plane rotations 0..150 step 30 deg, depth steps."""
     rng = np.random.RandomState(seed)
     out = np.zeros((n_cand, 4, 4))
     sel = rng.randint(0, cloud_xyz.shape[0], size=n_cand)
@@ -183,7 +204,7 @@ def make_candidates(cloud_xyz, cloud_normal, n_cand, seed=0, hand_depth=0.03, ap
         major = np.cross(minor, approach)
         R0 = np.stack([approach, major, minor], 1)
         # cone direction: rotate about a random in-plane axis by up to 60 deg
-        ang = rng.uniform(0, np.pi / 3)
+        ang = rng.uniform(0, np.deg2rad(cone_deg))
         phi = rng.uniform(0, 2 * np.pi)
         axis = np.array([0, np.cos(phi), np.sin(phi)])
         K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])

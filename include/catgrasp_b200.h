@@ -41,8 +41,11 @@ typedef struct cg_sdf cg_sdf;   /* one Sdf3D grid resident in HBM             */
 /* ---- context ----------------------------------------------------------- */
 int         cg_ctx_create(int device, cg_ctx **out);
 void        cg_ctx_destroy(cg_ctx *ctx);
-/* Use a caller-owned cudaStream_t (passed as void*); NULL = context's own. */
+/* Enqueue on a caller-owned cudaStream_t (passed as void*).  NULL means the
+ * CUDA legacy default stream (stream 0), NOT the context's own stream; a new
+ * context starts on its own non-blocking stream (cg_ctx_use_own_stream).      */
 int         cg_ctx_set_stream(cg_ctx *ctx, void *cuda_stream);
+int         cg_ctx_use_own_stream(cg_ctx *ctx);
 int         cg_ctx_synchronize(cg_ctx *ctx);
 const char *cg_last_error(cg_ctx *ctx);
 const char *cg_version(void);

@@ -140,7 +140,8 @@ def test_predicter_dropin_surface(cuda, tmp_path):
     assert np.array_equal(npred.data_transformed["cloud_xyz_original"], rdt["cloud_xyz_original"])
     assert np.array_equal(npred.data_transformed["keep_ids"], rdt["keep_ids"])
     top2 = np.sort(rlogits, axis=-1)[..., -2:]
-    decisive = (top2[..., 1] - top2[..., 0]) > 2 * LOGIT_TOL          # Appendix A6: bins equal where the gap is decisive
+    tol = 2 * LOGIT_TOL * max(1.0, float(np.abs(rlogits).max()))
+    decisive = (top2[..., 1] - top2[..., 0]) > tol                    # Appendix A6: bins equal where the gap is decisive
     assert np.array_equal(nocs[decisive], rn[decisive])
     assert decisive.mean() > 0.9
     assert (nocs.min() >= -0.5) and (nocs.max() <= 0.49 + 1e-6)
@@ -170,28 +171,32 @@ def test_graspq_full_size_properties(cls_net):
 
 
 # ------------------------------------------------------------------ collision filter
-def _filter_case(seed, G, S, P1, P2, scale=(1, 1, 1)):
-    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile, random_rotation
+def _filter_case(seed, G, S, scale=(1, 1, 1), n_points=2400):
+    """A sparse pile; the grasp target is object 3: its points feed the open-gripper check, all other
+    points the enclosed (swept-volume) check; the canonical frame is the target's own frame, so the
+    symmetry transforms spin the candidates about the object like Utils.py:79-84."""
+    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile
     rng = np.random.RandomState(seed)
-    scene = make_pile(max(P1 + P2, 600), n_objects=6, seed=seed)
-    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], G, seed=seed + 1)
+    scene = make_pile(n_points, n_objects=6, seed=seed)
+    obj = scene["object_id"] == 3
+    p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
+    poses = make_candidates(p1, scene["cloud_normal"][obj], G, seed=seed + 1)
     sym = []
-    for k in range(S):                                      # nut-like symmetry set (Utils.py:79-84)
+    for k in range(S):                                      # nut symmetry set (Utils.py:79-84)
         T = np.eye(4)
         a = k * np.pi / 3
         T[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
         if k >= 6:
             T[:3, :3] = T[:3, :3] @ np.diag([1, -1, -1])
         sym.append(T)
-    nocs_pose = np.eye(4)
-    nocs_pose[:3, :3] = random_rotation(rng) @ np.diag(scale)
-    nocs_pose[:3, 3] = rng.normal(0, 0.001, 3)
+    nocs_pose = scene["object_poses"][3].copy()
+    nocs_pose[:3, :3] = nocs_pose[:3, :3] @ np.diag(scale)   # 9-DoF pose: rotation x per-axis scale
     canonical_to_nocs = np.eye(4)
-    canonical_to_nocs[:3, 3] = rng.normal(0, 0.001, 3)
+    canonical_to_nocs[:3, 3] = rng.normal(0, 0.0005, 3)
     inv = np.linalg.inv(nocs_pose @ canonical_to_nocs)
-    poses_can = np.stack([inv @ p for p in poses])          # so that canonical_to_cam * pose lands near the scene
+    poses_can = np.stack([inv @ p for p in poses])          # canonical_to_cam * pose_can == the camera-frame pose
     g = make_gripper_proxy()
-    return scene, poses_can, np.stack(sym), nocs_pose, canonical_to_nocs, g
+    return p1, p2, poses_can, np.stack(sym), nocs_pose, canonical_to_nocs, g
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -201,10 +206,9 @@ def test_filter_bit_exact_vs_oracle(cuda, mode, adjust, fdir, S, scale):
     from catgrasp_b200 import my_cpp
     from catgrasp_b200.sdf import Sdf3D
     from oracle import filter_ref
-    scene, poses, sym, nocs_pose, c2n, g = _filter_case(31 + S, 96, S, 700, 900, scale)
+    p1, p2, poses, sym, nocs_pose, c2n, g = _filter_case(43, 128, S, scale)
     so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
     se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
-    p1, p2 = scene["cloud_xyz"][:700], scene["cloud_xyz"][700:1600]
     st, off, out = my_cpp.filter_grasp_pose_raw(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, so, p1,
                                                 se, p2, sdf_mode=mode)
     rst, roff, rout = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode,
@@ -212,7 +216,9 @@ def test_filter_bit_exact_vs_oracle(cuda, mode, adjust, fdir, S, scale):
     assert np.array_equal(st, rst)
     assert np.array_equal(off, roff)
     assert np.array_equal(out.view(np.uint32), rout.view(np.uint32))
-    assert len(set(st.tolist())) >= 2           # the case exercises both accept and reject
+    assert (st == 0).any() and (st == 3).any()      # the case exercises accept and collision-reject ...
+    if adjust:
+        assert len(set(off[st == 0].tolist())) >= 2  # ... and more than one winning lateral offset
     # device-pointer entry gives the same answer
     dst, doff, dout = my_cpp.filter_grasp_pose_raw(torch.from_numpy(poses).cuda(), sym, nocs_pose, c2n,
                                                    g["gripper_in_grasp"], fdir, adjust, so, p1, se, p2, sdf_mode=mode)
@@ -225,7 +231,7 @@ def test_filter_k2_size_bit_exact_and_offsets(cuda):
     from catgrasp_b200.sdf import Sdf3D
     from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile
     from oracle import filter_ref
-    scene = make_pile(20000, seed=0)
+    scene = make_pile(20000, seed=1)
     obj = scene["object_id"] == 3
     p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
     poses = make_candidates(p1, scene["cloud_normal"][obj], 4096, seed=1)
@@ -252,12 +258,11 @@ def test_my_cpp_filterGraspPose_signature(cuda):
     """The 20-positional-argument call of grasp_sampler.py:216 works unchanged."""
     from catgrasp_b200 import my_cpp
     from catgrasp_b200.sdf import Sdf3D
-    scene, poses, sym, nocs_pose, c2n, g = _filter_case(77, 40, 2, 500, 500)
+    p1, p2, poses, sym, nocs_pose, c2n, g = _filter_case(43, 40, 2)
     so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
     se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
     my_cpp.register_gripper_sdf(g["open"]["V"], g["open"]["F"], so)
     my_cpp.register_gripper_sdf(g["enclosed"]["V"], g["enclosed"]["F"], se)
-    p1, p2 = scene["cloud_xyz"][:500], scene["cloud_xyz"][500:1000]
     res = my_cpp.filterGraspPose(list(poses), list(sym), nocs_pose, c2n, np.eye(4), np.eye(4), g["gripper_in_grasp"],
                                  True, False, True, [3] * 7, [-3] * 7, g["open"]["V"], g["open"]["F"],
                                  g["enclosed"]["V"], g["enclosed"]["F"], p1, p2, 0.0005, False)
