@@ -133,7 +133,7 @@ __global__ void nunocs_post_kernel(const float *__restrict__ logits, int P, int 
   }
   if (lane == 0) {
     const float res = 1.0f / (float)bins;          // bin_resolution, predicter.py:145
-    if (coords) coords[(size_t)p * 3 + ax] = (float)am * res - 0.5f;  // :146,:150
+    if (coords) coords[(size_t)p * 3 + ax] = __fsub_rn(__fmul_rn((float)am, res), 0.5f);  // :146 then :150, two roundings
     if (out_bins) out_bins[(size_t)p * 3 + ax] = am;
   }
   if (ax == 2 && conf_z) {
