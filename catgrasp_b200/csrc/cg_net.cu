@@ -55,29 +55,29 @@ extern "C" int cg_net_create(cg_ctx *ctx, int kind, int n_out, const float *blob
   net->kind = kind;
   net->n_out = n_out;
   net->blob_floats = blob_floats;
-  for (int i = 0; i < 3; i++) net->tc_w3[i] = nullptr;
+  for (int i = 0; i < 3; i++) net->tc_img[i] = nullptr;
   CG_CUDA(ctx, cudaMalloc(&net->blob_dev, blob_floats * sizeof(float)));
   CG_CUDA(ctx, cudaMemcpyAsync(net->blob_dev, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice,
                                ctx->stream));
   LayerDim d[L_COUNT];
   layer_dims(kind, n_out, d);
   size_t off = 0;
-  size_t w3_off[3];
+  size_t woff[L_COUNT];
   for (int i = 0; i < L_COUNT; i++) {
     net->L[i].K = d[i].K;
     net->L[i].C = d[i].C;
     net->L[i].Wt = net->blob_dev + off;
-    if (i == L_S3_C3) w3_off[0] = off;
-    if (i == L_SK_C3) w3_off[1] = off;
-    if (i == L_E_C3) w3_off[2] = off;
+    woff[i] = off;
     off += pad64((size_t)d[i].K * d[i].C);
     net->L[i].b = net->blob_dev + off;
     off += pad64((size_t)d[i].C);
   }
-  // tensor-core operand images of the three 128->1024 layers
+  // tensor-core operand images of the three trunks
+  const int l3[3] = {L_S3_C3, L_SK_C3, L_E_C3}, l2[3] = {L_S3_C2, L_SK_C2, L_E_C2}, l1[3] = {-1, L_SK_C1, -1};
   for (int i = 0; i < 3; i++) {
-    CG_CUDA(ctx, cudaMalloc(&net->tc_w3[i], cg_tc_w3_bytes()));
-    int rc = cg_tc_prepare_w3(ctx, blob_host + w3_off[i], net->tc_w3[i]);
+    CG_CUDA(ctx, cudaMalloc(&net->tc_img[i], cg_tc_image_bytes()));
+    int rc = cg_tc_prepare(ctx, blob_host + woff[l3[i]], blob_host + woff[l2[i]],
+                           l1[i] >= 0 ? blob_host + woff[l1[i]] : nullptr, net->tc_img[i]);
     if (rc != CG_OK) return rc;
   }
   CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -89,7 +89,7 @@ extern "C" void cg_net_destroy(cg_net *net) {
   if (!net) return;
   cudaSetDevice(net->ctx->device);
   cudaFree(net->blob_dev);
-  for (int i = 0; i < 3; i++) cudaFree(net->tc_w3[i]);
+  for (int i = 0; i < 3; i++) cudaFree(net->tc_img[i]);
   delete net;
 }
 
@@ -143,7 +143,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   // --- trunk A: STN3d convs + max (pointnet2.py:170-175)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.T3 = nullptr; a.l0 = L[L_S3_C1]; a.stage1_mode = 0; a.l1 = cg_layer{nullptr, nullptr, 0, 0}; a.T64 = nullptr;
-  a.l2 = L[L_S3_C2]; a.l3 = L[L_S3_C3]; a.l3_tc = net->tc_w3[0]; a.relu3 = 1; a.gmax_keys = w.gmax; a.pf_out = nullptr;
+  a.l2 = L[L_S3_C2]; a.l3 = L[L_S3_C3]; a.tc_img = net->tc_img[0]; a.relu3 = 1; a.gmax_keys = w.gmax; a.pf_out = nullptr;
   if ((rc = trunk_launch(ctx, a))) return rc;
   if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_S3_F1].Wt, L[L_S3_F1].b, 512, 1, 0, 1, w.f1))) return rc;
   if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_S3_F2].Wt, L[L_S3_F2].b, 256, 1, 0, 0, w.f2))) return rc;
@@ -151,7 +151,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   // --- trunk B: encoder conv1 + STNkd convs + max (pointnet2.py:252, :208-213)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.T3 = w.T3; a.l0 = L[L_E_C1]; a.stage1_mode = 1; a.l1 = L[L_SK_C1];
-  a.l2 = L[L_SK_C2]; a.l3 = L[L_SK_C3]; a.l3_tc = net->tc_w3[1]; a.relu3 = 1;
+  a.l2 = L[L_SK_C2]; a.l3 = L[L_SK_C3]; a.tc_img = net->tc_img[1]; a.relu3 = 1;
   if ((rc = trunk_launch(ctx, a))) return rc;
   if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_SK_F1].Wt, L[L_SK_F1].b, 512, 1, 0, 1, w.f1))) return rc;
   if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_SK_F2].Wt, L[L_SK_F2].b, 256, 1, 0, 0, w.f2))) return rc;
@@ -159,7 +159,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   // --- trunk C: conv1, @T64, conv2, conv3(+BN, no ReLU), max (pointnet2.py:252-265)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.stage1_mode = 2; a.T64 = w.T64; a.l1 = cg_layer{nullptr, nullptr, 64, 64};
-  a.l2 = L[L_E_C2]; a.l3 = L[L_E_C3]; a.l3_tc = net->tc_w3[2]; a.relu3 = 0; a.pf_out = pf_out;
+  a.l2 = L[L_E_C2]; a.l3 = L[L_E_C3]; a.tc_img = net->tc_img[2]; a.relu3 = 0; a.pf_out = pf_out;
   if ((rc = trunk_launch(ctx, a))) return rc;
   return CG_OK;
 }

@@ -1,22 +1,24 @@
-// cg_trunk_tc.cu -- tcgen05 "trunk" kernel (engine 1): same fused chain as cg_trunk_simt.cu, with the
-// 128 -> 1024 shared-MLP layer (91.5 % of the path's FLOPs) on the 5th-gen tensor cores.
+// cg_trunk_tc.cu -- tcgen05 "trunk" kernel (engine 1): the fused per-point shared-MLP chain + max of
+// cg_trunk_simt.cu with every layer that is a genuine dense contraction on the 5th-gen tensor cores.
 //
-// Contraction per 128-point tile and 128-channel chunk:   D[ch][pt] = sum_k W3[ch][k] * X3[pt][k]
-//   A = W3 chunk  (M = 128 channels, K-major)   B = X3 tile (N = 128 points, K-major)   K = 128
-//   D lives in TMEM: lane = channel, column = point  -> the max over points is a per-thread reduction
-//   over TMEM columns (tcgen05.ld 32x32b), no cross-lane shuffles, and the N x 1024 activation never
-//   leaves the SM.
+//   layer            UMMA (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM)         epilogue
+//   6 -> 64          fp32 FMA (K = 6 is not a tensor-core shape; thread = point)          -> X1 | X2 tile
+//   64 -> 64 (L1)    D1[pt][ch]   = X1[pt][k]  . W1[ch][k]    M=128 N=64  K=64          bias/ReLU -> X2 tile
+//   64 -> 128 (L2)   D2[pt][ch]   = X2[pt][k]  . W2[ch][k]    M=128 N=128 K=64          bias/ReLU -> X3 tile
+//   128 -> 1024 (L3) D3[ch][pt]   = W3c[ch][k] . X3[pt][k]    M=128 N=128 K=128, x8 chunks  bias/ReLU/max over points
 //
-// Precision: scores must stay within 1e-4 of the fp32 reference, which rules out one
-// bf16 pass (and leaves single-pass TF32 marginal).  Operands are therefore split x = hi + lo with
-// hi = bf16(x), lo = bf16(x - hi) and every product is accumulated as  hi*hi + hi*lo + lo*hi  in the fp32
-// TMEM accumulator (kind::f16, three UMMAs per K-step); the dropped lo*lo term is ~2^-16 relative.
+// L1/L2 put points on TMEM lanes, so a thread owns one point's channel row and writes it straight into the
+// next layer's K-major operand tile with 16-byte stores; L3 puts channels on lanes, so the max over the
+// tile's points is a per-thread reduction over TMEM columns and the N x 1024 activation never leaves the SM.
 //
-// Shared-memory operand layout = the canonical UMMA K-major SWIZZLE_128B layout: a K-block of 64 bf16 is
-// one 128-byte row per M/N index, rows in 8-row / 1024-byte swizzle atoms, 16-byte chunk index XOR (row & 7).
-// W3 is pre-arranged in exactly this image on the host (cg_tc_prepare_w3), so a chunk arrives with plain
-// 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier; the X3 tile is written in the same
-// layout by the epilogue of the 64 -> 128 layer.
+// Precision: scores must stay within 1e-4 of the fp32 reference, which rules out a single
+// bf16 pass.  Every operand is split x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) and each product is
+// accumulated as lo*hi + hi*lo + hi*hi in the fp32 accumulator (three UMMAs per K-step, lo*lo ~ 2^-16 dropped).
+//
+// Operand tiles use the canonical UMMA K-major SWIZZLE_128B layout (64 bf16 = one 128-byte row per M/N index,
+// 8-row / 1024-byte swizzle atoms, 16-byte chunk index XOR (row & 7)).  Weights are pre-arranged in that image
+// on the host, so they arrive with plain 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on mbarriers:
+// W1/W2 once per CTA, W3 as a stream of 16 KB pieces through a 4-slot ring filled by a dedicated producer warp.
 #include <cuda_bf16.h>
 
 #include "cg_trunk_common.cuh"
@@ -24,23 +26,20 @@
 namespace {
 using namespace cg_trunk;
 
-constexpr uint32_t PIECE = 16384;        // [128 rows x 64 bf16] one swizzled K-block
-constexpr uint32_t OPND = 4 * PIECE;     // {hi,lo} x {kb0,kb1} = 64 KB: one full K=128 operand tile
-constexpr uint32_t X3_OFF = 0;
-constexpr uint32_t RING_OFF = OPND;      // two 64 KB stages of W3 chunks
-constexpr uint32_t MISC_OFF = 3 * OPND;  // 192 KB
-constexpr int NCHUNK = 8;                // 1024 output channels / 128
-constexpr uint32_t TMEM_COLS = 256;      // two 128-column fp32 accumulators
-
-// scratch of the SIMT front layers; aliases the W3 ring, which is idle while they run
-struct Scratch {
-  float in_s[8 * TP];     //  4 KB
-  float regA[64 * TP];    // 32 KB
-  float regB[64 * TP];    // 32 KB
-  float w1s[64 * 64];     // 16 KB
-  float w2s[64 * 128];    // 32 KB
-};
-static_assert(sizeof(Scratch) <= 2 * OPND, "front-layer scratch must fit in the W3 ring");
+constexpr int NCW = 8;                     // compute warps
+constexpr int NTC = NCW * 32 + 32;         // + 1 producer warp = 288 threads
+constexpr uint32_t PIECE = 16384;          // [128 rows x 64 bf16] one swizzled K-block
+constexpr uint32_t X3_OFF = 0;             // [hi|lo][kb0|kb1] 64 KB; X1 ([hi|lo], K=64) aliases its first 32 KB
+constexpr uint32_t X2_OFF = 4 * PIECE;     // [hi|lo] 32 KB
+constexpr uint32_t W1_OFF = 6 * PIECE;     // [hi|lo][64 rows x 128 B] 16 KB
+constexpr uint32_t W2_OFF = 7 * PIECE;     // [hi|lo][128 rows x 128 B] 32 KB
+constexpr uint32_t RING_OFF = 9 * PIECE;   // 4 x 16 KB pieces of W3
+constexpr int NSLOT = 4;
+constexpr uint32_t MISC_OFF = RING_OFF + NSLOT * PIECE;   // 208 KB
+constexpr int NCHUNK = 8;                  // 1024 output channels / 128
+constexpr uint32_t TMEM_COLS = 512;        // D3 x2 (0..255), D1 (256..319), D2 (320..447)
+constexpr uint32_t D1_COL = 256, D2_COL = 320;
+constexpr uint32_t W3_IMG = NCHUNK * 4 * PIECE, W2_IMG = 2 * PIECE, W1_IMG = PIECE;
 
 struct Misc {
   uint32_t gmax_s[1024];
@@ -51,17 +50,19 @@ struct Misc {
   double pinv[12];
   double mean[6];
   double sden[6];
-  float T3[9];
+  float T3[12];
+  unsigned long long full_bar[NSLOT];   // W3 piece landed in ring slot
+  unsigned long long free_bar[NSLOT];   // UMMAs reading ring slot have completed
+  unsigned long long acc_bar[2];        // all UMMAs of the chunk accumulating into D3[buf] have completed
+  unsigned long long l1_bar, l2_bar, w_bar;
   uint32_t tmem_base;
-  unsigned long long full_bar[2];   // W3 chunk landed in ring stage s
-  unsigned long long done_bar[2];   // UMMAs of the chunk using stage s / accumulator s have completed
 };
 
 constexpr size_t SMEM_BYTES = MISC_OFF + sizeof(Misc) + 1024;  // + slack for manual 1024-byte alignment
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -88,21 +89,24 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start address (>>4), LBO = 1 (ignored for swizzled
 // K-major), SBO = 1024 B between 8-row groups, version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t idesc(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(id), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -126,78 +130,61 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
   for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
 
-// byte offset of element (row, k) of a K=128 bf16 operand tile, part 0 = hi, 1 = lo
-__host__ __device__ __forceinline__ uint32_t opnd_off(int part, int row, int k) {
-  const int kb = k >> 6, kk = k & 63;
-  return (uint32_t)part * (2 * PIECE) + (uint32_t)kb * PIECE + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u +
-         (uint32_t)(((kk >> 3) ^ (row & 7)) << 4) + (uint32_t)(kk & 7) * 2u;
+// byte offset of the 16-byte chunk `c16` (8 bf16) of row `row` inside one swizzled [rows x 64] K-block
+__host__ __device__ __forceinline__ uint32_t row_chunk_off(int row, int c16) {
+  return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
 }
 
-// 64 -> 128 layer (+bias, ReLU) whose output is written as the bf16 hi/lo UMMA operand tile X3[pt][ch]
-__device__ __forceinline__ void mlp_layer_to_umma(const float *__restrict__ hin, const float *__restrict__ w,
-                                                  const float *__restrict__ bias, unsigned char *__restrict__ x3,
-                                                  int tx, int ty) {
-  float acc[8][8];
+// split 8 fp32 values into bf16 hi / lo and store them as the two 16-byte chunks of an operand row
+__device__ __forceinline__ void store_hilo8(unsigned char *hi_dst, unsigned char *lo_dst, const float *v) {
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int i = 0; i < 8; i++)
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
-  const int p0 = ty * 4, p1 = 64 + ty * 4;
-  const int c0 = tx * 4, c1 = 64 + tx * 4;
-#pragma unroll 4
-  for (int k = 0; k < 64; k++) {
-    float a[8], b[8];
-    *reinterpret_cast<float4 *>(&a[0]) = *reinterpret_cast<const float4 *>(&hin[k * TP + p0]);
-    *reinterpret_cast<float4 *>(&a[4]) = *reinterpret_cast<const float4 *>(&hin[k * TP + p1]);
-    *reinterpret_cast<float4 *>(&b[0]) = *reinterpret_cast<const float4 *>(&w[k * 128 + c0]);
-    *reinterpret_cast<float4 *>(&b[4]) = *reinterpret_cast<const float4 *>(&w[k * 128 + c1]);
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-      for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  for (int j = 0; j < 4; j++) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
+  *reinterpret_cast<uint4 *>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// K = 64 layer: 4 K-steps x (x_lo*w_hi + x_hi*w_lo + x_hi*w_hi);  A = activations (M = 128 points), B = weights
+__device__ __forceinline__ void issue_k64(uint32_t d, uint32_t x_s, uint32_t x_part, uint32_t w_s, uint32_t w_part,
+                                          uint32_t id) {
+  uint32_t acc = 0u;
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int p = (i < 4) ? (p0 + i) : (p1 + i - 4);
-#pragma unroll
-    for (int q = 0; q < 2; q++) {   // channel quad: c0.. (K-block 0) / c1.. (K-block 1)
-      const int c = q ? c1 : c0;
-      unsigned short hi[4], lo[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const float v = fmaxf(acc[i][q * 4 + j] + bias[c + j], 0.f);
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
-        hi[j] = __bfloat16_as_ushort(h);
-        lo[j] = __bfloat16_as_ushort(l);
-      }
-      const uint32_t off = opnd_off(0, p, c);
-      *reinterpret_cast<uint2 *>(x3 + off) = make_uint2(hi[0] | ((uint32_t)hi[1] << 16), hi[2] | ((uint32_t)hi[3] << 16));
-      *reinterpret_cast<uint2 *>(x3 + off + 2 * PIECE) =
-          make_uint2(lo[0] | ((uint32_t)lo[1] << 16), lo[2] | ((uint32_t)lo[3] << 16));
-    }
+  for (int ks = 0; ks < 4; ks++) {
+    const uint32_t koff = (uint32_t)ks * 32u;
+    const uint64_t a_hi = umma_desc(x_s + koff), a_lo = umma_desc(x_s + x_part + koff);
+    const uint64_t b_hi = umma_desc(w_s + koff), b_lo = umma_desc(w_s + w_part + koff);
+    umma(d, a_lo, b_hi, id, acc);
+    umma(d, a_hi, b_lo, id, 1u);
+    umma(d, a_hi, b_hi, id, 1u);
+    acc = 1u;
   }
 }
 
-__global__ void __launch_bounds__(NT, 1) trunk_tc_kernel(const cg_trunk_args a, int tiles_per_cta) {
+__global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a, int tiles_per_cta) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char *x3 = smem + X3_OFF;
-  unsigned char *ring = smem + RING_OFF;
-  Scratch &F = *reinterpret_cast<Scratch *>(ring);
+  unsigned char *x3 = smem + X3_OFF, *x1 = smem + X3_OFF, *x2 = smem + X2_OFF;
+  unsigned char *w1 = smem + W1_OFF;
   Misc &S = *reinterpret_cast<Misc *>(smem + MISC_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tx = tid & 15, ty = tid >> 4;
   const int b = blockIdx.y;
   const int N = a.N;
   const int ntiles = (N + TP - 1) / TP;
   const int tile_begin = blockIdx.x * tiles_per_cta;
   const int tile_end = min(ntiles, tile_begin + tiles_per_cta);
   if (tile_begin >= tile_end) return;
+  const unsigned char *img = static_cast<const unsigned char *>(a.tc_img);
+  const bool has_l1 = a.stage1_mode != 0;
 
-  // ---- one-time setup: constants, mbarriers, TMEM ---------------------------
-  for (int i = tid; i < 1024; i += NT) S.gmax_s[i] = 0u;
-  for (int i = tid; i < 6 * 64; i += NT) S.w0[i] = a.l0.Wt[i];
+  // ---- one-time setup: constants, mbarriers, TMEM, resident weight images ---------------------------
+  for (int i = tid; i < 1024; i += NTC) S.gmax_s[i] = 0u;
+  for (int i = tid; i < 6 * 64; i += NTC) S.w0[i] = a.l0.Wt[i];
   if (tid < 64) {
     S.bias0[tid] = a.l0.b[tid];
     S.bias1[tid] = (a.stage1_mode == 1) ? a.l1.b[tid] : 0.f;
@@ -211,11 +198,30 @@ __global__ void __launch_bounds__(NT, 1) trunk_tc_kernel(const cg_trunk_args a, 
       S.sden[tid] = a.in.stdv ? (a.in.stdv[tid] + 1e-15) : 1.0;
     }
   }
+  if (a.stage1_mode == 2) {
+    // per-candidate feature transform as the B operand of L1:  B[j][k] = T64[k][j]   (pointnet2.py:257)
+    const float *T = a.T64 + (size_t)b * 4096;
+    for (int idx = tid; idx < 4096; idx += NTC) {
+      const int k = idx >> 6, j = idx & 63;
+      const float v = T[idx];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      const uint32_t off = row_chunk_off(j, k >> 3) + (uint32_t)(k & 7) * 2u;
+      *reinterpret_cast<__nv_bfloat16 *>(w1 + off) = h;
+      *reinterpret_cast<__nv_bfloat16 *>(w1 + 8192 + off) = l;
+    }
+    fence_proxy_async();
+  }
   if (tid == 0) {
-    mbar_init(smem_u32(&S.full_bar[0]), 1);
-    mbar_init(smem_u32(&S.full_bar[1]), 1);
-    mbar_init(smem_u32(&S.done_bar[0]), 1);
-    mbar_init(smem_u32(&S.done_bar[1]), 1);
+    for (int i = 0; i < NSLOT; i++) {
+      mbar_init(smem_u32(&S.full_bar[i]), 1);
+      mbar_init(smem_u32(&S.free_bar[i]), 1);
+    }
+    mbar_init(smem_u32(&S.acc_bar[0]), 1);
+    mbar_init(smem_u32(&S.acc_bar[1]), 1);
+    mbar_init(smem_u32(&S.l1_bar), 1);
+    mbar_init(smem_u32(&S.l2_bar), 1);
+    mbar_init(smem_u32(&S.w_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -228,149 +234,217 @@ __global__ void __launch_bounds__(NT, 1) trunk_tc_kernel(const cg_trunk_args a, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
-  const uint32_t full_bar[2] = {smem_u32(&S.full_bar[0]), smem_u32(&S.full_bar[1])};
-  const uint32_t done_bar[2] = {smem_u32(&S.done_bar[0]), smem_u32(&S.done_bar[1])};
-  uint32_t full_ph[2] = {0u, 0u}, done_ph[2] = {0u, 0u};
-  const unsigned char *w3img = static_cast<const unsigned char *>(a.l3_tc);
-  const uint32_t x3_s = smem_u32(x3), ring_s = smem_u32(ring);
+  const uint32_t x3_s = smem_u32(x3), x1_s = x3_s, x2_s = smem_u32(x2), w1_s = smem_u32(w1), w2_s = smem_u32(smem + W2_OFF);
+  const uint32_t ring_s = smem_u32(smem + RING_OFF);
 
-  for (int tile = tile_begin; tile < tile_end; tile++) {
-    // ================= front layers (fp32 SIMT), scratch aliases the idle W3 ring =================
-    if (a.stage1_mode != 0) {
-      const float *src = (a.stage1_mode == 1) ? a.l1.Wt : (a.T64 + (size_t)b * 4096);
-      for (int e = tid * 4; e < 4096; e += NT * 4) cp_async16(F.w1s + e, src + e);
-    }
-    for (int e = tid * 4; e < 8192; e += NT * 4) cp_async16(F.w2s + e, a.l2.Wt + e);
-    cp_async_commit();
-    if (tid < TP) {
-      int n = tile * TP + tid;
-      if (n >= N) n = N - 1;
-      float v[6];
-      if (a.in.x_direct) {
-        const float *xr = a.in.x_direct + ((size_t)b * N + n) * 6;
-#pragma unroll
-        for (int k = 0; k < 6; k++) v[k] = xr[k];
-      } else {
-        const int id = a.in.ids ? a.in.ids[(size_t)b * N + n] : n;
-        const double *px = a.in.cloud_xyz + (size_t)id * 3;
-        const double *pn = a.in.cloud_nrm + (size_t)id * 3;
-        const double x = px[0], y = px[1], z = px[2];
-        const double nx = pn[0], ny = pn[1], nz = pn[2];
-        const double *R = S.pinv;
-        double w[6];
-        w[0] = R[0] * x + R[1] * y + R[2] * z + R[9];
-        w[1] = R[3] * x + R[4] * y + R[5] * z + R[10];
-        w[2] = R[6] * x + R[7] * y + R[8] * z + R[11];
-        w[3] = R[0] * nx + R[1] * ny + R[2] * nz;
-        w[4] = R[3] * nx + R[4] * ny + R[5] * nz;
-        w[5] = R[6] * nx + R[7] * ny + R[8] * nz;
-#pragma unroll
-        for (int k = 0; k < 6; k++) v[k] = (float)((w[k] - S.mean[k]) / S.sden[k]);
+  if (warp == NCW) {
+    // ======================= producer warp: stream W3 pieces through the ring =======================
+    if (lane == 0) {
+      const int total = (tile_end - tile_begin) * NCHUNK * 4;
+      for (int g = 0; g < total; g++) {
+        const int slot = g & (NSLOT - 1);
+        mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> 2) & 1u) ^ 1u);   // first round passes immediately
+        const uint32_t fb = smem_u32(&S.full_bar[slot]);
+        mbar_expect_tx(fb, PIECE);
+        bulk_g2s(ring_s + (uint32_t)slot * PIECE, img + (size_t)(g & (NCHUNK * 4 - 1)) * PIECE, PIECE, fb);
       }
-      if (a.T3) {
-        const float x = v[0], y = v[1], z = v[2];
-        v[0] = fmaf(z, S.T3[6], fmaf(y, S.T3[3], x * S.T3[0]));
-        v[1] = fmaf(z, S.T3[7], fmaf(y, S.T3[4], x * S.T3[1]));
-        v[2] = fmaf(z, S.T3[8], fmaf(y, S.T3[5], x * S.T3[2]));
-      }
+    }
+  } else {
+    // ======================= compute warps =======================
+    if (tid == 0) {   // resident weights: W2 (and the shared W1 of the STNkd trunk)
+      const uint32_t wb = smem_u32(&S.w_bar);
+      mbar_expect_tx(wb, W2_IMG + (a.stage1_mode == 1 ? W1_IMG : 0u));
+      bulk_g2s(w2_s, img + W3_IMG, PIECE, wb);
+      bulk_g2s(w2_s + PIECE, img + W3_IMG + PIECE, PIECE, wb);
+      if (a.stage1_mode == 1) bulk_g2s(w1_s, img + W3_IMG + W2_IMG, W1_IMG, wb);
+    }
+    const int p = tid & 127, half = tid >> 7;       // L0 / L1 / L2 epilogues: thread = point, half = channel half
+    const int q = warp & 3;                         // TMEM lane quadrant of this warp
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    uint32_t g = 0;                                 // consumed W3 pieces (thread 0 only)
+    uint32_t acc_ph[2] = {0u, 0u}, l1_ph = 0u, l2_ph = 0u;
+    bool w_ready = false;
+
+    for (int tile = tile_begin; tile < tile_end; tile++) {
+      // ---------------- input rows + 6 -> 64 on the FMA pipe (thread = point, 32 channels) ----------------
+      {
+        int n = tile * TP + p;
+        if (n >= N) n = N - 1;   // duplicate a valid point: cannot change a max
+        float v[6];
+        if (a.in.x_direct) {
+          const float *xr = a.in.x_direct + ((size_t)b * N + n) * 6;
 #pragma unroll
-      for (int k = 0; k < 6; k++) F.in_s[k * TP + tid] = v[k];
-    }
-    __syncthreads();
-    float *h0 = (a.stage1_mode != 0) ? F.regA : F.regB;
-    mlp_layer<6, 64, 4, true, true>(F.in_s, S.w0, S.bias0, h0, tx, ty);
-    cp_async_wait<0>();
-    __syncthreads();
-    if (a.stage1_mode == 1) {
-      mlp_layer<64, 64, 4, true, true>(F.regA, F.w1s, S.bias1, F.regB, tx, ty);
-      __syncthreads();
-    } else if (a.stage1_mode == 2) {
-      mlp_layer<64, 64, 4, false, false>(F.regA, F.w1s, S.bias1, F.regB, tx, ty);
-      __syncthreads();
-    }
-    if (a.pf_out) {
-      const int p = tid & (TP - 1);
-      const int n = tile * TP + p;
-      if (n < N) {
-        float *dst = a.pf_out + ((size_t)b * N + n) * 64;
-        for (int c = (tid >> 7) * 4; c < 64; c += 8) {
-          float4 o = make_float4(F.regB[(c + 0) * TP + p], F.regB[(c + 1) * TP + p], F.regB[(c + 2) * TP + p],
-                                 F.regB[(c + 3) * TP + p]);
-          *reinterpret_cast<float4 *>(dst + c) = o;
+          for (int k = 0; k < 6; k++) v[k] = xr[k];
+        } else {
+          const int id = a.in.ids ? a.in.ids[(size_t)b * N + n] : n;
+          const double *px = a.in.cloud_xyz + (size_t)id * 3;
+          const double *pn = a.in.cloud_nrm + (size_t)id * 3;
+          const double x = px[0], y = px[1], z = px[2];
+          const double nx = pn[0], ny = pn[1], nz = pn[2];
+          const double *R = S.pinv;
+          double w[6];
+          w[0] = R[0] * x + R[1] * y + R[2] * z + R[9];
+          w[1] = R[3] * x + R[4] * y + R[5] * z + R[10];
+          w[2] = R[6] * x + R[7] * y + R[8] * z + R[11];
+          w[3] = R[0] * nx + R[1] * ny + R[2] * nz;
+          w[4] = R[3] * nx + R[4] * ny + R[5] * nz;
+          w[5] = R[6] * nx + R[7] * ny + R[8] * nz;
+#pragma unroll
+          for (int k = 0; k < 6; k++) v[k] = (float)((w[k] - S.mean[k]) / S.sden[k]);
+        }
+        if (a.T3) {  // xyz @ T3 (pointnet2.py:248), normals pass through (:245-250)
+          const float x = v[0], y = v[1], z = v[2];
+          v[0] = fmaf(z, S.T3[6], fmaf(y, S.T3[3], x * S.T3[0]));
+          v[1] = fmaf(z, S.T3[7], fmaf(y, S.T3[4], x * S.T3[1]));
+          v[2] = fmaf(z, S.T3[8], fmaf(y, S.T3[5], x * S.T3[2]));
+        }
+        unsigned char *dst = has_l1 ? x1 : x2;      // input tile of L1, or directly of L2 (STN3d trunk)
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          const int c0 = half * 32 + cc * 8;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[j] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 6; k++) {
+            const float4 wa = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0]);
+            const float4 wb = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0 + 4]);
+            o[0] = fmaf(v[k], wa.x, o[0]); o[1] = fmaf(v[k], wa.y, o[1]); o[2] = fmaf(v[k], wa.z, o[2]); o[3] = fmaf(v[k], wa.w, o[3]);
+            o[4] = fmaf(v[k], wb.x, o[4]); o[5] = fmaf(v[k], wb.y, o[5]); o[6] = fmaf(v[k], wb.z, o[6]); o[7] = fmaf(v[k], wb.w, o[7]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j] + S.bias0[c0 + j], 0.f);
+          const uint32_t off = row_chunk_off(p, c0 >> 3);
+          store_hilo8(dst + off, dst + PIECE + off, o);
         }
       }
-    }
-    mlp_layer_to_umma(F.regB, F.w2s, S.bias2, x3, tx, ty);
-    // generic-proxy writes (X3 tile, scratch) -> visible to / ordered before the async proxy (bulk copies, UMMA)
-    fence_proxy_async();
-    __syncthreads();
+      fence_proxy_async();   // generic-proxy tile writes -> visible to the async proxy (UMMA operand reads)
+      bar_compute();
 
-    // ================= 128 -> 1024 on tcgen05, fused bias/ReLU/max epilogue =================
-    if (tid == 0) {
-      mbar_expect_tx(full_bar[0], OPND);
-#pragma unroll
-      for (int pc = 0; pc < 4; pc++) bulk_g2s(ring_s + pc * PIECE, w3img + (size_t)pc * PIECE, PIECE, full_bar[0]);
-    }
-    for (int c = 0; c <= NCHUNK; c++) {
-      const int s = c & 1;
-      if (c < NCHUNK && tid == 0) {
-        mbar_wait(full_bar[s], full_ph[s]);
-        full_ph[s] ^= 1u;
+      // ---------------- L1: 64 -> 64 (STNkd conv1 + ReLU, or h @ T64) ----------------
+      if (has_l1) {
+        if (tid == 0) {
+          if (!w_ready) { mbar_wait(smem_u32(&S.w_bar), 0u); w_ready = true; }
+          tc_fence_after();
+          issue_k64(tmem_base + D1_COL, x1_s, PIECE, w1_s, 8192u, idesc(128, 64));
+          umma_commit(smem_u32(&S.l1_bar));
+        }
+        __syncwarp();
+        mbar_wait(smem_u32(&S.l1_bar), l1_ph);
+        l1_ph ^= 1u;
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)s * 128u;
-        const uint32_t a_base = ring_s + (uint32_t)s * OPND;
-        uint32_t acc = 0u;
+        {
+          float v[32];
+          tmem_ld32(tmem_base + lane_sel + D1_COL + (uint32_t)half * 32u, v);
+          if (a.stage1_mode == 1) {
 #pragma unroll
-        for (int kb = 0; kb < 2; kb++) {
+            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias1[half * 32 + j], 0.f);
+          }
+          if (a.pf_out) {   // PointNetSeg point feature (pointnet2.py:261)
+            const int n = tile * TP + p;
+            if (n < N) {
+              float4 *dstg = reinterpret_cast<float4 *>(a.pf_out + ((size_t)b * N + n) * 64 + half * 32);
 #pragma unroll
-          for (int ks = 0; ks < 4; ks++) {
-            const uint32_t koff = (uint32_t)kb * PIECE + (uint32_t)ks * 32u;
-            const uint64_t a_hi = umma_desc(a_base + koff), a_lo = umma_desc(a_base + 2 * PIECE + koff);
-            const uint64_t b_hi = umma_desc(x3_s + koff), b_lo = umma_desc(x3_s + 2 * PIECE + koff);
-            umma_bf16(d_tmem, a_lo, b_hi, acc);   // small terms first
-            umma_bf16(d_tmem, a_hi, b_lo, 1u);
-            umma_bf16(d_tmem, a_hi, b_hi, 1u);
-            acc = 1u;
+              for (int j = 0; j < 8; j++) dstg[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+          }
+#pragma unroll
+          for (int cc = 0; cc < 4; cc++) {
+            const uint32_t off = row_chunk_off(p, half * 4 + cc);
+            store_hilo8(x2 + off, x2 + PIECE + off, v + cc * 8);
           }
         }
-        umma_commit(done_bar[s]);
+        tc_fence_before();
+        fence_proxy_async();
+        bar_compute();
+      }
+
+      // ---------------- L2: 64 -> 128 + ReLU ----------------
+      if (tid == 0) {
+        if (!w_ready) { mbar_wait(smem_u32(&S.w_bar), 0u); w_ready = true; }
+        tc_fence_after();
+        issue_k64(tmem_base + D2_COL, x2_s, PIECE, w2_s, PIECE, idesc(128, 128));
+        umma_commit(smem_u32(&S.l2_bar));
       }
       __syncwarp();
-      if (c >= 1) {
-        const int pb = s ^ 1, pc = c - 1;           // accumulator / chunk whose UMMAs were issued last round
-        mbar_wait(done_bar[pb], done_ph[pb]);
-        done_ph[pb] ^= 1u;
-        tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)pb * 128u + (uint32_t)half * 64u;
-        float m = -INFINITY;
+      mbar_wait(smem_u32(&S.l2_bar), l2_ph);
+      l2_ph ^= 1u;
+      tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-          float v[32];
-          tmem_ld32(taddr + (uint32_t)j * 32u, v);
+      for (int j32 = 0; j32 < 2; j32++) {
+        float v[32];
+        tmem_ld32(tmem_base + lane_sel + D2_COL + (uint32_t)half * 64u + (uint32_t)j32 * 32u, v);
 #pragma unroll
-          for (int i = 0; i < 32; i++) m = fmaxf(m, v[i]);
+        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias2[half * 64 + j32 * 32 + j], 0.f);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc++) {
+          // channel = half*64 + j32*32 + cc*8 ..  ->  K-block `half`, 16-byte chunk j32*4 + cc
+          const uint32_t off = (uint32_t)half * PIECE + row_chunk_off(p, j32 * 4 + cc);
+          store_hilo8(x3 + off, x3 + 2 * PIECE + off, v + cc * 8);
         }
-        const int ch = pc * 128 + q * 32 + lane;
-        m += __ldg(&a.l3.b[ch]);
-        if (a.relu3) m = fmaxf(m, 0.f);
-        atomicMax(&S.gmax_s[ch], cg_f2key(m));
-        tc_fence_before();
       }
-      __syncthreads();   // accumulator pb drained, ring stage pb free
-      if (tid == 0 && c + 1 < NCHUNK) {
-        const int ns = s ^ 1;
-        mbar_expect_tx(full_bar[ns], OPND);
-        const unsigned char *src = w3img + (size_t)(c + 1) * OPND;
+      tc_fence_before();
+      fence_proxy_async();
+      bar_compute();
+
+      // ---------------- L3: 128 -> 1024 in 8 chunks, fused bias / ReLU / max over the tile's points ----------------
+      for (int c = 0; c <= NCHUNK; c++) {
+        const int s = c & 1;
+        if (c < NCHUNK && tid == 0) {
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)s * 128u;
+          constexpr uint32_t id = idesc(128, 128);
 #pragma unroll
-        for (int pc = 0; pc < 4; pc++)
-          bulk_g2s(ring_s + (uint32_t)ns * OPND + pc * PIECE, src + (size_t)pc * PIECE, PIECE, full_bar[ns]);
+          for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
+            const int slot = g & (NSLOT - 1);
+            mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
+            tc_fence_after();
+            const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
+            const uint32_t kb = (uint32_t)(i & 1) * PIECE;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              const uint32_t koff = (uint32_t)ks * 32u;
+              const uint64_t ad = umma_desc(a_s + koff);
+              if (i < 2) {
+                umma(d, ad, umma_desc(x3_s + 2 * PIECE + kb + koff), id, (i | ks) ? 1u : 0u);   // w_hi * x_lo
+                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_hi * x_hi
+              } else {
+                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_lo * x_hi
+              }
+            }
+            umma_commit(smem_u32(&S.free_bar[slot]));
+            g++;
+          }
+          umma_commit(smem_u32(&S.acc_bar[s]));
+        }
+        __syncwarp();
+        if (c >= 1) {
+          const int pb = s ^ 1, pc = c - 1;     // accumulator / chunk issued in the previous round
+          mbar_wait(smem_u32(&S.acc_bar[pb]), acc_ph[pb]);
+          acc_ph[pb] ^= 1u;
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_sel + (uint32_t)pb * 128u + (uint32_t)half * 64u;
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)j * 32u, v);
+#pragma unroll
+            for (int i = 0; i < 32; i++) m = fmaxf(m, v[i]);
+          }
+          const int ch = pc * 128 + q * 32 + lane;
+          m += __ldg(&a.l3.b[ch]);   // bias is constant over points: add after the max
+          if (a.relu3) m = fmaxf(m, 0.f);
+          atomicMax(&S.gmax_s[ch], cg_f2key(m));
+          tc_fence_before();
+        }
+        bar_compute();   // accumulator pb drained before it is overwritten two rounds later
       }
+      // every UMMA of this tile has completed: X1/X2/X3 may be rewritten
     }
-    // all UMMAs of this tile have completed and been consumed: ring and X3 are free again
+    for (int i = tid; i < 1024; i += NCW * 32) atomicMax(&a.gmax_keys[(size_t)b * 1024 + i], S.gmax_s[i]);
   }
 
-  for (int i = tid; i < 1024; i += NT) atomicMax(&a.gmax_keys[(size_t)b * 1024 + i], S.gmax_s[i]);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -392,24 +466,31 @@ float bf16_to_f(unsigned short h) {
   return f;
 }
 
+// B-operand / A-operand image of a folded layer: rows = output channels [c0, c0+rows), K-major, nkb K-blocks of 64,
+// layout [hi|lo][kb][rows x 128 B swizzled].  Wt is [K][C] (k-major rows, as in the weight blob).
+void pack_image(const float *Wt, int C, int c0, int rows, int nkb, unsigned char *dst) {
+  const size_t kb_bytes = (size_t)rows * 128, part_bytes = kb_bytes * nkb;
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < nkb * 64; k++) {
+      const float w = Wt[(size_t)k * C + c0 + r];
+      const unsigned short hi = bf16_rne(w);
+      const unsigned short lo = bf16_rne(w - bf16_to_f(hi));
+      const size_t off = (size_t)(k >> 6) * kb_bytes + row_chunk_off(r, (k & 63) >> 3) + (size_t)(k & 7) * 2;
+      memcpy(dst + off, &hi, 2);
+      memcpy(dst + part_bytes + off, &lo, 2);
+    }
+}
+
 }  // namespace
 
-size_t cg_tc_w3_bytes() { return (size_t)NCHUNK * OPND; }
+size_t cg_tc_image_bytes() { return (size_t)W3_IMG + W2_IMG + W1_IMG; }
 
-// Wt_host: [128][1024] folded fp32 (k-major rows).  Device image: per 128-channel chunk one 64 KB operand tile
-// [hi|lo][kb][128 rows x 128 B swizzled].
-int cg_tc_prepare_w3(cg_ctx *ctx, const float *Wt_host, void *dst_dev) {
-  std::vector<unsigned char> img(cg_tc_w3_bytes());
-  for (int ch = 0; ch < NCHUNK; ch++)
-    for (int r = 0; r < 128; r++)
-      for (int k = 0; k < 128; k++) {
-        const float w = Wt_host[(size_t)k * 1024 + ch * 128 + r];
-        const unsigned short hi = bf16_rne(w);
-        const unsigned short lo = bf16_rne(w - bf16_to_f(hi));
-        unsigned char *base = img.data() + (size_t)ch * OPND;
-        memcpy(base + opnd_off(0, r, k), &hi, 2);
-        memcpy(base + opnd_off(1, r, k), &lo, 2);
-      }
+int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *Wt1, void *dst_dev) {
+  std::vector<unsigned char> img(cg_tc_image_bytes(), 0);
+  // W3: per 128-channel chunk one 64 KB tile whose four 16 KB pieces are [hi kb0][hi kb1][lo kb0][lo kb1]
+  for (int ch = 0; ch < NCHUNK; ch++) pack_image(Wt3, 1024, ch * 128, 128, 2, img.data() + (size_t)ch * 4 * PIECE);
+  pack_image(Wt2, 128, 0, 128, 1, img.data() + W3_IMG);            // [hi 16 KB][lo 16 KB]
+  if (Wt1) pack_image(Wt1, 64, 0, 64, 1, img.data() + W3_IMG + W2_IMG);   // [hi 8 KB][lo 8 KB]
   CG_CUDA(ctx, cudaMemcpyAsync(dst_dev, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
   CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // img goes out of scope
   return CG_OK;
@@ -418,7 +499,7 @@ int cg_tc_prepare_w3(cg_ctx *ctx, const float *Wt_host, void *dst_dev) {
 int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_REQUIRE(ctx, a.B > 0 && a.N > 0, "trunk: B,N must be positive");
   CG_REQUIRE(ctx, a.B <= 65535, "trunk: B > 65535 must be chunked by the caller");
-  CG_REQUIRE(ctx, a.l3_tc != nullptr, "trunk: tensor-core weight image missing");
+  CG_REQUIRE(ctx, a.tc_img != nullptr, "trunk: tensor-core weight image missing");
   static bool attr_set = false;
   if (!attr_set) {
     CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -429,7 +510,7 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   while ((long)a.B * splits < 4L * ctx->num_sms && splits < ntiles) splits *= 2;
   const int tiles_per_cta = (ntiles + splits - 1) / splits;
   dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, a.B);
-  trunk_tc_kernel<<<grid, NT, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
+  trunk_tc_kernel<<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
   CG_LAUNCH_CHECK(ctx);
   return CG_OK;
 }
