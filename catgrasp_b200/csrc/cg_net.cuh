@@ -56,6 +56,7 @@ struct cg_trunk_args {
   int relu3;
   uint32_t *gmax_keys;  // (B,1024) order-preserving keys, zero-initialised by the launcher
   float *pf_out;        // (B,N,64) stage-1 output (PointNetSeg point feature) or nullptr
+  unsigned long long *dbg;  // optional per-CTA cycle counters (CG_TRUNK_DEBUG=1), else nullptr
 };
 
 int cg_trunk_launch_simt(cg_ctx *ctx, const cg_trunk_args &a);

@@ -20,6 +20,7 @@
 // on the host, so they arrive with plain 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on mbarriers:
 // W1/W2 once per CTA, W3 as a stream of 16 KB pieces through a 4-slot ring filled by a dedicated producer warp.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "cg_trunk_common.cuh"
 
@@ -264,8 +265,10 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     uint32_t g = 0;                                 // consumed W3 pieces (thread 0 only)
     uint32_t acc_ph[2] = {0u, 0u}, l1_ph = 0u, l2_ph = 0u;
     bool w_ready = false;
+    long long t_full = 0, t_front = 0, t_acc = 0, t_l12 = 0, t_tile0 = 0, t_all = clock64();
 
     for (int tile = tile_begin; tile < tile_end; tile++) {
+      t_tile0 = clock64();
       // ---------------- input rows + 6 -> 64 on the FMA pipe (thread = point, 32 channels) ----------------
       {
         int n = tile * TP + p;
@@ -330,7 +333,9 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           umma_commit(smem_u32(&S.l1_bar));
         }
         __syncwarp();
+        const long long tw1 = clock64();
         mbar_wait(smem_u32(&S.l1_bar), l1_ph);
+        t_l12 += clock64() - tw1;
         l1_ph ^= 1u;
         tc_fence_after();
         {
@@ -367,7 +372,9 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
         umma_commit(smem_u32(&S.l2_bar));
       }
       __syncwarp();
+      const long long tw2 = clock64();
       mbar_wait(smem_u32(&S.l2_bar), l2_ph);
+      t_l12 += clock64() - tw2;
       l2_ph ^= 1u;
       tc_fence_after();
 #pragma unroll
@@ -387,6 +394,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       fence_proxy_async();
       bar_compute();
 
+      t_front += clock64() - t_tile0;
       // ---------------- L3: 128 -> 1024 in 8 chunks, fused bias / ReLU / max over the tile's points ----------------
       for (int c = 0; c <= NCHUNK; c++) {
         const int s = c & 1;
@@ -397,7 +405,9 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
           for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
             const int slot = g & (NSLOT - 1);
+            const long long tw = clock64();
             mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
+            t_full += clock64() - tw;
             tc_fence_after();
             const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
             const uint32_t kb = (uint32_t)(i & 1) * PIECE;
@@ -420,7 +430,9 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
         __syncwarp();
         if (c >= 1) {
           const int pb = s ^ 1, pc = c - 1;     // accumulator / chunk issued in the previous round
+          const long long tw = clock64();
           mbar_wait(smem_u32(&S.acc_bar[pb]), acc_ph[pb]);
+          t_acc += clock64() - tw;
           acc_ph[pb] ^= 1u;
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_sel + (uint32_t)pb * 128u + (uint32_t)half * 64u;
@@ -443,6 +455,10 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       // every UMMA of this tile has completed: X1/X2/X3 may be rewritten
     }
     for (int i = tid; i < 1024; i += NCW * 32) atomicMax(&a.gmax_keys[(size_t)b * 1024 + i], S.gmax_s[i]);
+    if (a.dbg && tid == 0) {
+      unsigned long long *d = a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      d[0] = clock64() - t_all; d[1] = t_front; d[2] = t_full; d[3] = t_acc; d[4] = t_l12; d[5] = tile_end - tile_begin;
+    }
   }
 
   tc_fence_before();
@@ -510,6 +526,28 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   while ((long)a.B * splits < 4L * ctx->num_sms && splits < ntiles) splits *= 2;
   const int tiles_per_cta = (ntiles + splits - 1) / splits;
   dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, a.B);
+  static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
+  if (debug) {
+    cg_trunk_args ad = a;
+    const size_t n = (size_t)grid.x * grid.y;
+    unsigned long long *d_dbg = nullptr;
+    CG_CUDA(ctx, cudaMalloc(&d_dbg, n * 64));
+    CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n * 64, ctx->stream));
+    ad.dbg = d_dbg;
+    trunk_tc_kernel<<<grid, NTC, SMEM_BYTES, ctx->stream>>>(ad, tiles_per_cta);
+    CG_LAUNCH_CHECK(ctx);
+    std::vector<unsigned long long> h(n * 8);
+    CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_dbg);
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t i = 0; i < n; i++)
+      for (int k = 0; k < 6; k++) s[k] += (double)h[i * 8 + k];
+    const double tiles = s[5] > 0 ? s[5] : 1;
+    fprintf(stderr, "[trunk_tc dbg] CTAs=%zu tiles=%.0f  per tile: total %.0f  front %.0f (l1/l2 wait %.0f)  full-wait %.0f  acc-wait %.0f cycles\n",
+            n, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles, s[3] / tiles);
+    return CG_OK;
+  }
   trunk_tc_kernel<<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
   CG_LAUNCH_CHECK(ctx);
   return CG_OK;
