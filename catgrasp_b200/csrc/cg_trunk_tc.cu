@@ -19,6 +19,11 @@
 // 8-row / 1024-byte swizzle atoms, 16-byte chunk index XOR (row & 7)).  Weights are pre-arranged in that image
 // on the host, so they arrive with plain 1-D bulk copies (cp.async.bulk -> UBLKCP) completing on mbarriers:
 // W1/W2 once per CTA, W3 as a stream of 16 KB pieces through a 4-slot ring filled by a dedicated producer warp.
+//
+// Warp roles (448 threads, 1 CTA / SM):  warps 0-7 "front" (6->64 FMA layer, L1/L2 epilogues, thread = point),
+// warps 8-11 "max" (L3 epilogue, thread = channel), warp 12 W3 producer, warp 13 UMMA issuer.  All hand-overs
+// are mbarriers, so the front layers of tile t+1 (FMA + L1 + L2 UMMAs) run in the shadow of tile t's L3 stream;
+// only the L2 epilogue (TMEM -> X3) has to wait for the previous tile's last UMMA.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -27,11 +32,15 @@
 namespace {
 using namespace cg_trunk;
 
-constexpr int NCW = 8;                     // compute warps
-constexpr int NTC = NCW * 32 + 32;         // + 1 producer warp = 288 threads
+constexpr int NFRONT = 8;                  // front warps 0..7  : thread = (point, channel half); L0 + L1/L2 epilogues
+constexpr int NMAXW = 4;                   // max warps   8..11 : thread = channel; L3 max-epilogue
+constexpr int PROD_WARP = NFRONT + NMAXW;  // warp 12: W3 ring producer
+constexpr int MMA_WARP = PROD_WARP + 1;    // warp 13: UMMA issuer
+constexpr int NTC = (MMA_WARP + 1) * 32;   // 448 threads
+constexpr int NFT = NFRONT * 32;           // 256 front threads
 constexpr uint32_t PIECE = 16384;          // [128 rows x 64 bf16] one swizzled K-block
-constexpr uint32_t X3_OFF = 0;             // [hi|lo][kb0|kb1] 64 KB; X1 ([hi|lo], K=64) aliases its first 32 KB
-constexpr uint32_t X2_OFF = 4 * PIECE;     // [hi|lo] 32 KB
+constexpr uint32_t X3_OFF = 0;             // [hi|lo][kb0|kb1] 64 KB  L3 input tile
+constexpr uint32_t XA_OFF = 4 * PIECE;     // [hi|lo] 32 KB: X1 (L1 input), then X2 (L2 input) of the same tile
 constexpr uint32_t W1_OFF = 6 * PIECE;     // [hi|lo][64 rows x 128 B] 16 KB
 constexpr uint32_t W2_OFF = 7 * PIECE;     // [hi|lo][128 rows x 128 B] 32 KB
 constexpr uint32_t RING_OFF = 9 * PIECE;   // 4 x 16 KB pieces of W3
@@ -43,7 +52,6 @@ constexpr uint32_t D1_COL = 256, D2_COL = 320;
 constexpr uint32_t W3_IMG = NCHUNK * 4 * PIECE, W2_IMG = 2 * PIECE, W1_IMG = PIECE;
 
 struct Misc {
-  uint32_t gmax_s[1024];
   float w0[6 * 64];
   float bias0[64];
   float bias1[64];
@@ -52,10 +60,14 @@ struct Misc {
   double mean[6];
   double sden[6];
   float T3[12];
-  unsigned long long full_bar[NSLOT];   // W3 piece landed in ring slot
-  unsigned long long free_bar[NSLOT];   // UMMAs reading ring slot have completed
-  unsigned long long acc_bar[2];        // all UMMAs of the chunk accumulating into D3[buf] have completed
-  unsigned long long l1_bar, l2_bar, w_bar;
+  unsigned long long full_bar[NSLOT];     // producer -> MMA : W3 piece landed in ring slot
+  unsigned long long free_bar[NSLOT];     // MMA -> producer : UMMAs reading the slot have completed
+  unsigned long long acc_bar[2];          // MMA -> max      : chunk accumulated into D3[buf]
+  unsigned long long accfree_bar[2];      // max -> MMA      : D3[buf] drained (one arrival per max warp)
+  unsigned long long x1_bar, x2_bar, x3_bar;   // front -> MMA : XA holds X1 / XA holds X2 / X3 written
+  unsigned long long l1_bar, l2_bar;      // MMA -> front    : D1 / D2 complete
+  unsigned long long tile_bar;            // MMA -> front    : every L3 UMMA of the tile completed (X3 reusable)
+  unsigned long long w_bar;               // resident W1/W2 images landed
   uint32_t tmem_base;
 };
 
@@ -90,7 +102,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_front() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start address (>>4), LBO = 1 (ignored for swizzled
 // K-major), SBO = 1024 B between 8-row groups, version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
@@ -170,8 +185,7 @@ __device__ __forceinline__ void issue_k64(uint32_t d, uint32_t x_s, uint32_t x_p
 __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a, int tiles_per_cta) {
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char *x3 = smem + X3_OFF, *x1 = smem + X3_OFF, *x2 = smem + X2_OFF;
-  unsigned char *w1 = smem + W1_OFF;
+  unsigned char *x3 = smem + X3_OFF, *xa = smem + XA_OFF, *w1 = smem + W1_OFF;
   Misc &S = *reinterpret_cast<Misc *>(smem + MISC_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
@@ -180,11 +194,11 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
   const int tile_begin = blockIdx.x * tiles_per_cta;
   const int tile_end = min(ntiles, tile_begin + tiles_per_cta);
   if (tile_begin >= tile_end) return;
+  const int my_tiles = tile_end - tile_begin;
   const unsigned char *img = static_cast<const unsigned char *>(a.tc_img);
   const bool has_l1 = a.stage1_mode != 0;
 
-  // ---- one-time setup: constants, mbarriers, TMEM, resident weight images ---------------------------
-  for (int i = tid; i < 1024; i += NTC) S.gmax_s[i] = 0u;
+  // ---- one-time setup: constants, mbarriers, TMEM, per-candidate T64 operand ---------------------------
   for (int i = tid; i < 6 * 64; i += NTC) S.w0[i] = a.l0.Wt[i];
   if (tid < 64) {
     S.bias0[tid] = a.l0.b[tid];
@@ -218,10 +232,16 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       mbar_init(smem_u32(&S.full_bar[i]), 1);
       mbar_init(smem_u32(&S.free_bar[i]), 1);
     }
-    mbar_init(smem_u32(&S.acc_bar[0]), 1);
-    mbar_init(smem_u32(&S.acc_bar[1]), 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(smem_u32(&S.acc_bar[i]), 1);
+      mbar_init(smem_u32(&S.accfree_bar[i]), NMAXW);
+    }
+    mbar_init(smem_u32(&S.x1_bar), 1);
+    mbar_init(smem_u32(&S.x2_bar), 1);
+    mbar_init(smem_u32(&S.x3_bar), 1);
     mbar_init(smem_u32(&S.l1_bar), 1);
     mbar_init(smem_u32(&S.l2_bar), 1);
+    mbar_init(smem_u32(&S.tile_bar), 1);
     mbar_init(smem_u32(&S.w_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -235,13 +255,13 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
-  const uint32_t x3_s = smem_u32(x3), x1_s = x3_s, x2_s = smem_u32(x2), w1_s = smem_u32(w1), w2_s = smem_u32(smem + W2_OFF);
+  const uint32_t x3_s = smem_u32(x3), xa_s = smem_u32(xa), w1_s = smem_u32(w1), w2_s = smem_u32(smem + W2_OFF);
   const uint32_t ring_s = smem_u32(smem + RING_OFF);
 
-  if (warp == NCW) {
-    // ======================= producer warp: stream W3 pieces through the ring =======================
+  if (warp == PROD_WARP) {
+    // ======================= producer: stream W3 pieces through the ring =======================
     if (lane == 0) {
-      const int total = (tile_end - tile_begin) * NCHUNK * 4;
+      const int total = my_tiles * NCHUNK * 4;
       for (int g = 0; g < total; g++) {
         const int slot = g & (NSLOT - 1);
         mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> 2) & 1u) ^ 1u);   // first round passes immediately
@@ -250,26 +270,138 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
         bulk_g2s(ring_s + (uint32_t)slot * PIECE, img + (size_t)(g & (NCHUNK * 4 - 1)) * PIECE, PIECE, fb);
       }
     }
-  } else {
-    // ======================= compute warps =======================
-    if (tid == 0) {   // resident weights: W2 (and the shared W1 of the STNkd trunk)
-      const uint32_t wb = smem_u32(&S.w_bar);
+  } else if (warp == MMA_WARP) {
+    // ======================= UMMA issuer (one thread) =======================
+    if (lane == 0) {
+      const uint32_t wb = smem_u32(&S.w_bar);   // resident weights: W2 (and the shared W1 of the STNkd trunk)
       mbar_expect_tx(wb, W2_IMG + (a.stage1_mode == 1 ? W1_IMG : 0u));
       bulk_g2s(w2_s, img + W3_IMG, PIECE, wb);
       bulk_g2s(w2_s + PIECE, img + W3_IMG + PIECE, PIECE, wb);
       if (a.stage1_mode == 1) bulk_g2s(w1_s, img + W3_IMG + W2_IMG, W1_IMG, wb);
+      mbar_wait(wb, 0u);
+      uint32_t g = 0;                       // consumed W3 pieces
+      uint32_t ph_x1 = 0u, ph_x2 = 0u;      // parities of the next x1 / x2 hand-over
+      long long t_all = clock64(), t_full = 0, t_x3 = 0, t_accf = 0, t_x12 = 0;
+      // front layers of the first tile
+      if (has_l1) {
+        mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
+        tc_fence_after();
+        issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
+        umma_commit(smem_u32(&S.l1_bar));
+      }
+      mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
+      tc_fence_after();
+      issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
+      umma_commit(smem_u32(&S.l2_bar));
+      for (int it = 0; it < my_tiles; it++) {
+        long long tw = clock64();
+        mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
+        t_x3 += clock64() - tw;
+        const bool has_next = it + 1 < my_tiles;
+        for (int c = 0; c < NCHUNK; c++) {
+          const int buf = c & 1;
+          const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
+          if (use >= 1u) {
+            tw = clock64();
+            mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
+            t_accf += clock64() - tw;
+          }
+          tc_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)buf * 128u;
+          constexpr uint32_t id = idesc(128, 128);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
+            const int slot = g & (NSLOT - 1);
+            tw = clock64();
+            mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
+            t_full += clock64() - tw;
+            tc_fence_after();
+            const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
+            const uint32_t kb = (uint32_t)(i & 1) * PIECE;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              const uint32_t koff = (uint32_t)ks * 32u;
+              const uint64_t ad = umma_desc(a_s + koff);
+              if (i < 2) {
+                umma(d, ad, umma_desc(x3_s + 2 * PIECE + kb + koff), id, (i | ks) ? 1u : 0u);   // w_hi * x_lo
+                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_hi * x_hi
+              } else {
+                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_lo * x_hi
+              }
+            }
+            umma_commit(smem_u32(&S.free_bar[slot]));
+            g++;
+          }
+          umma_commit(smem_u32(&S.acc_bar[buf]));
+          if (c == NCHUNK - 1) umma_commit(smem_u32(&S.tile_bar));
+          // front layers of the NEXT tile run in the shadow of this tile's L3 stream
+          if (has_next && c == 2 && has_l1) {
+            tw = clock64();
+            mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
+            t_x12 += clock64() - tw;
+            tc_fence_after();
+            issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
+            umma_commit(smem_u32(&S.l1_bar));
+          }
+          if (has_next && c == 4) {
+            tw = clock64();
+            mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
+            t_x12 += clock64() - tw;
+            tc_fence_after();
+            issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
+            umma_commit(smem_u32(&S.l2_bar));
+          }
+        }
+      }
+      if (a.dbg) {
+        unsigned long long *dd = a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_full; dd[3] = t_accf; dd[4] = t_x12; dd[5] = my_tiles;
+      }
     }
-    const int p = tid & 127, half = tid >> 7;       // L0 / L1 / L2 epilogues: thread = point, half = channel half
+  } else if (warp >= NFRONT) {
+    // ======================= max warps: L3 epilogue, thread = output channel =======================
+    const int q = warp & 3;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float run[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; c++) run[c] = -INFINITY;
+    for (int it = 0; it < my_tiles; it++) {
+#pragma unroll
+      for (int c = 0; c < NCHUNK; c++) {
+        const int buf = c & 1;
+        const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);
+        mbar_wait(smem_u32(&S.acc_bar[buf]), use & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_sel + (uint32_t)buf * 128u;
+        float m = run[c];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)j * 32u, v);
+#pragma unroll
+          for (int i = 0; i < 32; i++) m = fmaxf(m, v[i]);
+        }
+        run[c] = m;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&S.accfree_bar[buf]));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCHUNK; c++) {
+      const int ch = c * 128 + q * 32 + lane;
+      float m = run[c] + __ldg(&a.l3.b[ch]);   // bias is constant over points: add after the max
+      if (a.relu3) m = fmaxf(m, 0.f);
+      atomicMax(&a.gmax_keys[(size_t)b * 1024 + ch], cg_f2key(m));
+    }
+  } else {
+    // ======================= front warps: thread = (point, channel half) =======================
+    const int p = tid & 127, half = tid >> 7;
     const int q = warp & 3;                         // TMEM lane quadrant of this warp
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    uint32_t g = 0;                                 // consumed W3 pieces (thread 0 only)
-    uint32_t acc_ph[2] = {0u, 0u}, l1_ph = 0u, l2_ph = 0u;
-    bool w_ready = false;
-    long long t_full = 0, t_front = 0, t_acc = 0, t_l12 = 0, t_tile0 = 0, t_all = clock64();
-
-    for (int tile = tile_begin; tile < tile_end; tile++) {
-      t_tile0 = clock64();
-      // ---------------- input rows + 6 -> 64 on the FMA pipe (thread = point, 32 channels) ----------------
+    for (int it = 0; it < my_tiles; it++) {
+      const int tile = tile_begin + it;
+      // ---------------- input rows + 6 -> 64 on the FMA pipe ----------------
       {
         int n = tile * TP + p;
         if (n >= N) n = N - 1;   // duplicate a valid point: cannot change a max
@@ -301,7 +433,6 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           v[1] = fmaf(z, S.T3[7], fmaf(y, S.T3[4], x * S.T3[1]));
           v[2] = fmaf(z, S.T3[8], fmaf(y, S.T3[5], x * S.T3[2]));
         }
-        unsigned char *dst = has_l1 ? x1 : x2;      // input tile of L1, or directly of L2 (STN3d trunk)
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) {
           const int c0 = half * 32 + cc * 8;
@@ -318,25 +449,16 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
           for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j] + S.bias0[c0 + j], 0.f);
           const uint32_t off = row_chunk_off(p, c0 >> 3);
-          store_hilo8(dst + off, dst + PIECE + off, o);
+          store_hilo8(xa + off, xa + PIECE + off, o);
         }
       }
       fence_proxy_async();   // generic-proxy tile writes -> visible to the async proxy (UMMA operand reads)
-      bar_compute();
+      bar_front();
+      if (tid == 0) mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
 
-      // ---------------- L1: 64 -> 64 (STNkd conv1 + ReLU, or h @ T64) ----------------
+      // ---------------- L1 epilogue: D1 -> (bias, ReLU | nothing) -> XA as the L2 input ----------------
       if (has_l1) {
-        if (tid == 0) {
-          if (!w_ready) { mbar_wait(smem_u32(&S.w_bar), 0u); w_ready = true; }
-          tc_fence_after();
-          issue_k64(tmem_base + D1_COL, x1_s, PIECE, w1_s, 8192u, idesc(128, 64));
-          umma_commit(smem_u32(&S.l1_bar));
-        }
-        __syncwarp();
-        const long long tw1 = clock64();
-        mbar_wait(smem_u32(&S.l1_bar), l1_ph);
-        t_l12 += clock64() - tw1;
-        l1_ph ^= 1u;
+        mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
         tc_fence_after();
         {
           float v[32];
@@ -356,26 +478,18 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
           for (int cc = 0; cc < 4; cc++) {
             const uint32_t off = row_chunk_off(p, half * 4 + cc);
-            store_hilo8(x2 + off, x2 + PIECE + off, v + cc * 8);
+            store_hilo8(xa + off, xa + PIECE + off, v + cc * 8);
           }
         }
         tc_fence_before();
         fence_proxy_async();
-        bar_compute();
+        bar_front();
+        if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
       }
 
-      // ---------------- L2: 64 -> 128 + ReLU ----------------
-      if (tid == 0) {
-        if (!w_ready) { mbar_wait(smem_u32(&S.w_bar), 0u); w_ready = true; }
-        tc_fence_after();
-        issue_k64(tmem_base + D2_COL, x2_s, PIECE, w2_s, PIECE, idesc(128, 128));
-        umma_commit(smem_u32(&S.l2_bar));
-      }
-      __syncwarp();
-      const long long tw2 = clock64();
-      mbar_wait(smem_u32(&S.l2_bar), l2_ph);
-      t_l12 += clock64() - tw2;
-      l2_ph ^= 1u;
+      // ---------------- L2 epilogue: D2 -> bias, ReLU -> X3 (once the previous tile's L3 has let go of it) -------
+      mbar_wait(smem_u32(&S.l2_bar), (uint32_t)it & 1u);
+      if (it >= 1) mbar_wait(smem_u32(&S.tile_bar), (uint32_t)(it - 1) & 1u);
       tc_fence_after();
 #pragma unroll
       for (int j32 = 0; j32 < 2; j32++) {
@@ -392,72 +506,8 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       }
       tc_fence_before();
       fence_proxy_async();
-      bar_compute();
-
-      t_front += clock64() - t_tile0;
-      // ---------------- L3: 128 -> 1024 in 8 chunks, fused bias / ReLU / max over the tile's points ----------------
-      for (int c = 0; c <= NCHUNK; c++) {
-        const int s = c & 1;
-        if (c < NCHUNK && tid == 0) {
-          tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)s * 128u;
-          constexpr uint32_t id = idesc(128, 128);
-#pragma unroll
-          for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
-            const int slot = g & (NSLOT - 1);
-            const long long tw = clock64();
-            mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
-            t_full += clock64() - tw;
-            tc_fence_after();
-            const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
-            const uint32_t kb = (uint32_t)(i & 1) * PIECE;
-#pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-              const uint32_t koff = (uint32_t)ks * 32u;
-              const uint64_t ad = umma_desc(a_s + koff);
-              if (i < 2) {
-                umma(d, ad, umma_desc(x3_s + 2 * PIECE + kb + koff), id, (i | ks) ? 1u : 0u);   // w_hi * x_lo
-                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_hi * x_hi
-              } else {
-                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_lo * x_hi
-              }
-            }
-            umma_commit(smem_u32(&S.free_bar[slot]));
-            g++;
-          }
-          umma_commit(smem_u32(&S.acc_bar[s]));
-        }
-        __syncwarp();
-        if (c >= 1) {
-          const int pb = s ^ 1, pc = c - 1;     // accumulator / chunk issued in the previous round
-          const long long tw = clock64();
-          mbar_wait(smem_u32(&S.acc_bar[pb]), acc_ph[pb]);
-          t_acc += clock64() - tw;
-          acc_ph[pb] ^= 1u;
-          tc_fence_after();
-          const uint32_t taddr = tmem_base + lane_sel + (uint32_t)pb * 128u + (uint32_t)half * 64u;
-          float m = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)j * 32u, v);
-#pragma unroll
-            for (int i = 0; i < 32; i++) m = fmaxf(m, v[i]);
-          }
-          const int ch = pc * 128 + q * 32 + lane;
-          m += __ldg(&a.l3.b[ch]);   // bias is constant over points: add after the max
-          if (a.relu3) m = fmaxf(m, 0.f);
-          atomicMax(&S.gmax_s[ch], cg_f2key(m));
-          tc_fence_before();
-        }
-        bar_compute();   // accumulator pb drained before it is overwritten two rounds later
-      }
-      // every UMMA of this tile has completed: X1/X2/X3 may be rewritten
-    }
-    for (int i = tid; i < 1024; i += NCW * 32) atomicMax(&a.gmax_keys[(size_t)b * 1024 + i], S.gmax_s[i]);
-    if (a.dbg && tid == 0) {
-      unsigned long long *d = a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
-      d[0] = clock64() - t_all; d[1] = t_front; d[2] = t_full; d[3] = t_acc; d[4] = t_l12; d[5] = tile_end - tile_begin;
+      bar_front();
+      if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
     }
   }
 
@@ -544,7 +594,7 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
     for (size_t i = 0; i < n; i++)
       for (int k = 0; k < 6; k++) s[k] += (double)h[i * 8 + k];
     const double tiles = s[5] > 0 ? s[5] : 1;
-    fprintf(stderr, "[trunk_tc dbg] CTAs=%zu tiles=%.0f  per tile: total %.0f  front %.0f (l1/l2 wait %.0f)  full-wait %.0f  acc-wait %.0f cycles\n",
+    fprintf(stderr, "[trunk_tc dbg] CTAs=%zu tiles=%.0f  MMA thread per tile: total %.0f  x3-wait %.0f  x1/x2-wait %.0f  full-wait %.0f  accfree-wait %.0f cycles\n",
             n, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles, s[3] / tiles);
     return CG_OK;
   }
