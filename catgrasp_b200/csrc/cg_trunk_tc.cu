@@ -125,6 +125,17 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(id), "r"(accumulate)
       : "memory");
 }
+// true in exactly one (converged-warp) lane; the compiler treats the guarded region as single-threaded, so
+// warp-uniform operands stay in uniform registers instead of going through per-lane R2UR broadcast loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -260,64 +271,66 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 
   if (warp == PROD_WARP) {
     // ======================= producer: stream W3 pieces through the ring =======================
-    if (lane == 0) {
-      const int total = my_tiles * NCHUNK * 4;
-      for (int g = 0; g < total; g++) {
-        const int slot = g & (NSLOT - 1);
-        mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> 2) & 1u) ^ 1u);   // first round passes immediately
+    const int total = my_tiles * NCHUNK * 4;
+    for (int g = 0; g < total; g++) {
+      const int slot = g & (NSLOT - 1);
+      mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> 2) & 1u) ^ 1u);   // first round passes immediately
+      if (elect_one()) {
         const uint32_t fb = smem_u32(&S.full_bar[slot]);
         mbar_expect_tx(fb, PIECE);
         bulk_g2s(ring_s + (uint32_t)slot * PIECE, img + (size_t)(g & (NCHUNK * 4 - 1)) * PIECE, PIECE, fb);
       }
+      __syncwarp();
     }
   } else if (warp == MMA_WARP) {
-    // ======================= UMMA issuer (one thread) =======================
-    if (lane == 0) {
-      const uint32_t wb = smem_u32(&S.w_bar);   // resident weights: W2 (and the shared W1 of the STNkd trunk)
+    // ======================= UMMA issuer: the warp stays converged, one elected lane issues =======================
+    const uint32_t wb = smem_u32(&S.w_bar);   // resident weights: W2 (and the shared W1 of the STNkd trunk)
+    if (elect_one()) {
       mbar_expect_tx(wb, W2_IMG + (a.stage1_mode == 1 ? W1_IMG : 0u));
       bulk_g2s(w2_s, img + W3_IMG, PIECE, wb);
       bulk_g2s(w2_s + PIECE, img + W3_IMG + PIECE, PIECE, wb);
       if (a.stage1_mode == 1) bulk_g2s(w1_s, img + W3_IMG + W2_IMG, W1_IMG, wb);
-      mbar_wait(wb, 0u);
-      uint32_t g = 0;                       // consumed W3 pieces
-      uint32_t ph_x1 = 0u, ph_x2 = 0u;      // parities of the next x1 / x2 hand-over
-      long long t_all = clock64(), t_full = 0, t_x3 = 0, t_accf = 0, t_x12 = 0;
-      // front layers of the first tile
-      if (has_l1) {
-        mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
-        tc_fence_after();
-        issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
-        umma_commit(smem_u32(&S.l1_bar));
-      }
-      mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
+    }
+    __syncwarp();
+    mbar_wait(wb, 0u);
+    uint32_t g = 0;                       // consumed W3 pieces
+    uint32_t ph_x1 = 0u, ph_x2 = 0u;      // parities of the next x1 / x2 hand-over
+    const uint32_t l1b = smem_u32(&S.l1_bar), l2b = smem_u32(&S.l2_bar);
+    // front layers of the first tile
+    if (has_l1) {
+      mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
       tc_fence_after();
+      if (elect_one()) {
+        issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
+        umma_commit(l1b);
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
+    tc_fence_after();
+    if (elect_one()) {
       issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
-      umma_commit(smem_u32(&S.l2_bar));
-      for (int it = 0; it < my_tiles; it++) {
-        long long tw = clock64();
-        mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
-        t_x3 += clock64() - tw;
-        const bool has_next = it + 1 < my_tiles;
-        for (int c = 0; c < NCHUNK; c++) {
-          const int buf = c & 1;
-          const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
-          if (use >= 1u) {
-            tw = clock64();
-            mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
-            t_accf += clock64() - tw;
-          }
-          tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)buf * 128u;
-          constexpr uint32_t id = idesc(128, 128);
+      umma_commit(l2b);
+    }
+    __syncwarp();
+    for (int it = 0; it < my_tiles; it++) {
+      mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
+      const bool has_next = it + 1 < my_tiles;
+      for (int c = 0; c < NCHUNK; c++) {
+        const int buf = c & 1;
+        const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
+        if (use >= 1u) mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)buf * 128u;
+        constexpr uint32_t id = idesc(128, 128);
 #pragma unroll
-          for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
-            const int slot = g & (NSLOT - 1);
-            tw = clock64();
-            mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
-            t_full += clock64() - tw;
-            tc_fence_after();
-            const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
-            const uint32_t kb = (uint32_t)(i & 1) * PIECE;
+        for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
+          const int slot = g & (NSLOT - 1);
+          mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
+          tc_fence_after();
+          const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
+          const uint32_t kb = (uint32_t)(i & 1) * PIECE;
+          if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
               const uint32_t koff = (uint32_t)ks * 32u;
@@ -330,32 +343,33 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
               }
             }
             umma_commit(smem_u32(&S.free_bar[slot]));
-            g++;
+            if (i == 3) {
+              umma_commit(smem_u32(&S.acc_bar[buf]));
+              if (c == NCHUNK - 1) umma_commit(smem_u32(&S.tile_bar));
+            }
           }
-          umma_commit(smem_u32(&S.acc_bar[buf]));
-          if (c == NCHUNK - 1) umma_commit(smem_u32(&S.tile_bar));
-          // front layers of the NEXT tile run in the shadow of this tile's L3 stream
-          if (has_next && c == 2 && has_l1) {
-            tw = clock64();
-            mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
-            t_x12 += clock64() - tw;
-            tc_fence_after();
-            issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
-            umma_commit(smem_u32(&S.l1_bar));
-          }
-          if (has_next && c == 4) {
-            tw = clock64();
-            mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
-            t_x12 += clock64() - tw;
-            tc_fence_after();
-            issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
-            umma_commit(smem_u32(&S.l2_bar));
-          }
+          __syncwarp();
+          g++;
         }
-      }
-      if (a.dbg) {
-        unsigned long long *dd = a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
-        dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_full; dd[3] = t_accf; dd[4] = t_x12; dd[5] = my_tiles;
+        // front layers of the NEXT tile run in the shadow of this tile's L3 stream
+        if (has_next && c == 2 && has_l1) {
+          mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
+          tc_fence_after();
+          if (elect_one()) {
+            issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
+            umma_commit(l1b);
+          }
+          __syncwarp();
+        }
+        if (has_next && c == 4) {
+          mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
+          tc_fence_after();
+          if (elect_one()) {
+            issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
+            umma_commit(l2b);
+          }
+          __syncwarp();
+        }
       }
     }
   } else if (warp >= NFRONT) {
