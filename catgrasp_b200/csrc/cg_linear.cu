@@ -87,6 +87,98 @@ __global__ void __launch_bounds__(256) linear_kernel(const float *__restrict__ X
   }
 }
 
+
+// Larger register tile for the wide FC layers: 64 x 128 outputs per CTA, 4 x 8 per thread, BK = 16, global->register
+// prefetch of the next k-tile while the current one is consumed from shared memory.
+constexpr int LM = 64, LN = 128, LK = 16;
+
+__global__ void __launch_bounds__(256) linear_wide_kernel(const float *__restrict__ X, int M, int K,
+                                                           const float *__restrict__ Wt,
+                                                           const float *__restrict__ bias, int N, int relu,
+                                                           int bias_row_div, int x_is_keys,
+                                                           float *__restrict__ Y) {
+  __shared__ __align__(16) float xs[2][LK][LM + 4];
+  __shared__ __align__(16) float ws[2][LK][LN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;            // 16 x 16 threads: ty -> 4 rows, tx -> 8 cols (2 x float4)
+  const int m0 = blockIdx.y * LM, n0 = blockIdx.x * LN;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+  // X tile 64 x 16: thread -> row (tid >> 2), 4 consecutive k ((tid & 3) * 4)
+  const int xr = tid >> 2, xk = (tid & 3) * 4;
+  // W tile 16 x 128: thread -> k row (tid >> 4), 8 consecutive n ((tid & 15) * 8)
+  const int wr = tid >> 4, wn = (tid & 15) * 8;
+  const bool xrow_ok = (m0 + xr) < M;
+  const float *xp = X + (size_t)(m0 + xr) * K + xk;
+  float4 xreg = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 wreg0 = xreg, wreg1 = xreg;
+  const bool vecN = ((N & 3) == 0);
+  auto gload = [&](int k0) {
+    if (xrow_ok) {
+      xreg = *reinterpret_cast<const float4 *>(xp + k0);
+      if (x_is_keys) {
+        xreg.x = cg_key2f(__float_as_uint(xreg.x)); xreg.y = cg_key2f(__float_as_uint(xreg.y));
+        xreg.z = cg_key2f(__float_as_uint(xreg.z)); xreg.w = cg_key2f(__float_as_uint(xreg.w));
+      }
+    }
+    const float *wp = Wt + (size_t)(k0 + wr) * N + n0 + wn;
+    if (vecN && n0 + wn + 8 <= N) {
+      wreg0 = *reinterpret_cast<const float4 *>(wp);
+      wreg1 = *reinterpret_cast<const float4 *>(wp + 4);
+    } else {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) t[q] = (n0 + wn + q < N) ? wp[q] : 0.f;
+      wreg0 = make_float4(t[0], t[1], t[2], t[3]);
+      wreg1 = make_float4(t[4], t[5], t[6], t[7]);
+    }
+  };
+  auto sstore = [&](int buf) {
+    xs[buf][xk + 0][xr] = xreg.x; xs[buf][xk + 1][xr] = xreg.y; xs[buf][xk + 2][xr] = xreg.z; xs[buf][xk + 3][xr] = xreg.w;
+    *reinterpret_cast<float4 *>(&ws[buf][wr][wn]) = wreg0;
+    *reinterpret_cast<float4 *>(&ws[buf][wr][wn + 4]) = wreg1;
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nk = K / LK;
+  for (int kt = 0; kt < nk; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * LK);
+#pragma unroll
+    for (int kk = 0; kk < LK; kk++) {
+      const float4 a = *reinterpret_cast<const float4 *>(&xs[buf][kk][ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4 *>(&ws[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4 *>(&ws[buf][kk][64 + tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const float *brow = bias ? (bias + (size_t)(bias_row_div > 0 ? (m / bias_row_div) : 0) * N) : nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int n = n0 + ((j < 4) ? (tx * 4 + j) : (64 + tx * 4 + j - 4));
+      if (n >= N) continue;
+      float v = acc[i][j] + (brow ? brow[n] : 0.f);
+      if (relu) v = fmaxf(v, 0.f);
+      Y[(size_t)m * N + n] = v;
+    }
+  }
+}
+
 // softmax over C <= 32 classes, one warp per row (predicter.py:86-90)
 __global__ void softmax_kernel(const float *__restrict__ logits, int B, int C, float *__restrict__ probs,
                                int32_t *__restrict__ label) {
@@ -150,6 +242,13 @@ __global__ void nunocs_post_kernel(const float *__restrict__ logits, int P, int 
 int cg_linear_launch(cg_ctx *ctx, const float *X, int M, int K, const float *Wt, const float *bias, int N,
                      int relu, int bias_row_div, int x_is_keys, float *Y) {
   CG_REQUIRE(ctx, M > 0 && K > 0 && N > 0, "linear: bad shape");
+  const long wide_ctas = (long)((N + LN - 1) / LN) * ((M + LM - 1) / LM);
+  if (N >= 128 && (K % LK) == 0 && (K % 4) == 0 && wide_ctas >= ctx->num_sms) {
+    dim3 gridw((N + LN - 1) / LN, (M + LM - 1) / LM);
+    linear_wide_kernel<<<gridw, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
+    CG_LAUNCH_CHECK(ctx);
+    return CG_OK;
+  }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
   linear_kernel<<<grid, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
   CG_LAUNCH_CHECK(ctx);
