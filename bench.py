@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--candidates", type=int, default=4096, help="candidates per GPU")
     ap.add_argument("--scene-pts", type=int, default=20000)
     ap.add_argument("--nunocs-pts", type=int, default=8192)
-    ap.add_argument("--engine", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 (default: library default)")
+    ap.add_argument("--engine", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 3-pass bf16, 2 tcgen05 2-pass fp16 (default: library default)")
     ap.add_argument("--cpu-sample", type=int, default=192, help="candidates in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -349,7 +349,7 @@ def main():
     peak = peaks["bf16_tflops_sustained"]
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "trunk (fused shared-MLP 6-64-[64]-128-1024 + max)",
-                "engine": ["fp32-simt", "tcgen05"][ctx.get_engine()],
+                "engine": ["fp32-simt", "tcgen05-bf16x3", "tcgen05-f16x2"][ctx.get_engine()],
                 "launches_timed": int(trunk_n), "avg_launch_ms": per_launch_ms,
                 "share_of_step": trunk_ms / ms, "peak_source": f"{peaks['source']} bf16 dense, sustained",
                 "frac_of_burst_peak": achieved / peaks["bf16_tflops"]}

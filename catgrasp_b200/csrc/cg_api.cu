@@ -64,7 +64,7 @@ extern "C" void cg_ctx_reset_launch_count(cg_ctx *ctx) { if (ctx) ctx->launches 
 
 extern "C" int cg_ctx_set_engine(cg_ctx *ctx, int engine) {
   if (!ctx) return CG_EINVAL;
-  CG_REQUIRE(ctx, engine == 0 || engine == 1, "engine must be 0 (fp32 SIMT) or 1 (tcgen05)");
+  CG_REQUIRE(ctx, engine >= 0 && engine <= 2, "engine must be 0 (fp32 SIMT), 1 (tcgen05 3-pass) or 2 (tcgen05 2-pass)");
   ctx->engine = engine;
   return CG_OK;
 }

@@ -102,7 +102,7 @@ int trunk_launch(cg_ctx *ctx, const cg_trunk_args &a) {
     CG_CUDA(ctx, cudaEventCreate(&e1));
     CG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   }
-  const int rc = ctx->engine == 1 ? cg_trunk_launch_tc(ctx, a) : cg_trunk_launch_simt(ctx, a);
+  const int rc = ctx->engine >= 1 ? cg_trunk_launch_tc(ctx, a) : cg_trunk_launch_simt(ctx, a);
   if (ctx->prof) {
     CG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     ctx->prof_events.emplace_back(e0, e1);

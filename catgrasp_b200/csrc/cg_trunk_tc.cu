@@ -25,6 +25,7 @@
 // are mbarriers, so the front layers of tile t+1 (FMA + L1 + L2 UMMAs) run in the shadow of tile t's L3 stream;
 // only the L2 epilogue (TMEM -> X3) has to wait for the previous tile's last UMMA.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "cg_trunk_common.cuh"
@@ -50,6 +51,8 @@ constexpr int NCHUNK = 8;                  // 1024 output channels / 128
 constexpr uint32_t TMEM_COLS = 512;        // D3 x2 (0..255), D1 (256..319), D2 (320..447)
 constexpr uint32_t D1_COL = 256, D2_COL = 320;
 constexpr uint32_t W3_IMG = NCHUNK * 4 * PIECE, W2_IMG = 2 * PIECE, W1_IMG = PIECE;
+constexpr uint32_t W3H_OFF = W3_IMG + W2_IMG + W1_IMG;   // fp16 single-term image of W3 (2-pass engine)
+constexpr uint32_t W3H_IMG = NCHUNK * 2 * PIECE;
 
 struct Misc {
   float w0[6 * 64];
@@ -113,8 +116,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor: D = f32 (bit 4), A = B = bf16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t idesc(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+constexpr uint32_t idesc(uint32_t M, uint32_t N, uint32_t a_fmt = 1u, uint32_t b_fmt = 1u) {   // fmt: 0 = f16, 1 = bf16
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
@@ -162,6 +165,43 @@ __host__ __device__ __forceinline__ uint32_t row_chunk_off(int row, int c16) {
   return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
 }
 
+// pack 8 fp32 values into 4+4 words of bf16 (or fp16) hi / lo pairs
+template <bool FP16>
+__device__ __forceinline__ void pack_hilo8(const float *v, uint32_t *h, uint32_t *l) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (FP16) {
+      const float a0 = fminf(v[2 * j], 65504.f), a1 = fminf(v[2 * j + 1], 65504.f);   // inputs are post-ReLU (>= 0)
+      const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+      const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+      h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    } else {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+  }
+}
+
+// fp16 flavour (2-pass engine: tcgen05 kind::f16 needs A and B in the same 16-bit format; mixing f16 x bf16 traps).
+// hi is clamped to the fp16 range so that an outlier saturates instead of turning into inf.
+__device__ __forceinline__ void store_hilo8_f16(unsigned char *hi_dst, unsigned char *lo_dst, const float *v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float a0 = fminf(v[2 * j], 65504.f), a1 = fminf(v[2 * j + 1], 65504.f);   // inputs are post-ReLU (>= 0)
+    const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
+    const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+    h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+    l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4 *>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4 *>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // split 8 fp32 values into bf16 hi / lo and store them as the two 16-byte chunks of an operand row
 __device__ __forceinline__ void store_hilo8(unsigned char *hi_dst, unsigned char *lo_dst, const float *v) {
   uint32_t h[4], l[4];
@@ -193,7 +233,11 @@ __device__ __forceinline__ void issue_k64(uint32_t d, uint32_t x_s, uint32_t x_p
   }
 }
 
+// PASSES = 3: W3 = bf16 hi + lo, products lo*hi + hi*lo + hi*hi (near-fp32).
+// PASSES = 2: W3 = one fp16 term (11-bit mantissa, rounding error 2^-12 per weight), X3 = fp16 hi + lo.
+template <int PASSES>
 __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a, int tiles_per_cta) {
+  constexpr int PPC = (PASSES == 3) ? 4 : 2;   // W3 ring pieces per 128-channel chunk
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char *x3 = smem + X3_OFF, *xa = smem + XA_OFF, *w1 = smem + W1_OFF;
@@ -221,7 +265,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     if (tid == 0) pose_inverse(a.in.poses + (size_t)b * 16, S.pinv);
     if (tid < 6) {
       S.mean[tid] = a.in.mean ? a.in.mean[tid] : 0.0;
-      S.sden[tid] = a.in.stdv ? (a.in.stdv[tid] + 1e-15) : 1.0;
+      S.sden[tid] = a.in.stdv ? 1.0 / (a.in.stdv[tid] + 1e-15) : 1.0;   // reciprocal: the hot loop multiplies
     }
   }
   if (a.stage1_mode == 2) {
@@ -271,14 +315,15 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 
   if (warp == PROD_WARP) {
     // ======================= producer: stream W3 pieces through the ring =======================
-    const int total = my_tiles * NCHUNK * 4;
+    const int total = my_tiles * NCHUNK * PPC;
+    const unsigned char *w3src = img + (PASSES == 3 ? 0u : W3H_OFF);
     for (int g = 0; g < total; g++) {
       const int slot = g & (NSLOT - 1);
       mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> 2) & 1u) ^ 1u);   // first round passes immediately
       if (elect_one()) {
         const uint32_t fb = smem_u32(&S.full_bar[slot]);
         mbar_expect_tx(fb, PIECE);
-        bulk_g2s(ring_s + (uint32_t)slot * PIECE, img + (size_t)(g & (NCHUNK * 4 - 1)) * PIECE, PIECE, fb);
+        bulk_g2s(ring_s + (uint32_t)slot * PIECE, w3src + (size_t)(g & (NCHUNK * PPC - 1)) * PIECE, PIECE, fb);
       }
       __syncwarp();
     }
@@ -295,6 +340,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     mbar_wait(wb, 0u);
     uint32_t g = 0;                       // consumed W3 pieces
     uint32_t ph_x1 = 0u, ph_x2 = 0u;      // parities of the next x1 / x2 hand-over
+    long long t_all = clock64(), t_x3 = 0, t_full = 0, t_accf = 0, t_x12 = 0, tw;
     const uint32_t l1b = smem_u32(&S.l1_bar), l2b = smem_u32(&S.l2_bar);
     // front layers of the first tile
     if (has_l1) {
@@ -314,19 +360,25 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     }
     __syncwarp();
     for (int it = 0; it < my_tiles; it++) {
+      tw = clock64();
       mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
+      t_x3 += clock64() - tw;
       const bool has_next = it + 1 < my_tiles;
       for (int c = 0; c < NCHUNK; c++) {
         const int buf = c & 1;
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
+        tw = clock64();
         if (use >= 1u) mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
+        t_accf += clock64() - tw;
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)buf * 128u;
-        constexpr uint32_t id = idesc(128, 128);
+        constexpr uint32_t id = (PASSES == 3) ? idesc(128, 128) : idesc(128, 128, 0u, 0u);   // bf16 x bf16 | f16 x f16
 #pragma unroll
-        for (int i = 0; i < 4; i++) {      // pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1
+        for (int i = 0; i < PPC; i++) {    // 3-pass pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1;  2-pass: W3 kb0, kb1
           const int slot = g & (NSLOT - 1);
+          tw = clock64();
           mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
+          t_full += clock64() - tw;
           tc_fence_after();
           const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
           const uint32_t kb = (uint32_t)(i & 1) * PIECE;
@@ -335,15 +387,15 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
             for (int ks = 0; ks < 4; ks++) {
               const uint32_t koff = (uint32_t)ks * 32u;
               const uint64_t ad = umma_desc(a_s + koff);
-              if (i < 2) {
-                umma(d, ad, umma_desc(x3_s + 2 * PIECE + kb + koff), id, (i | ks) ? 1u : 0u);   // w_hi * x_lo
-                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_hi * x_hi
+              if (PASSES == 2 || i < 2) {
+                umma(d, ad, umma_desc(x3_s + 2 * PIECE + kb + koff), id, (i | ks) ? 1u : 0u);   // w(_hi) * x_lo
+                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w(_hi) * x_hi
               } else {
                 umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_lo * x_hi
               }
             }
             umma_commit(smem_u32(&S.free_bar[slot]));
-            if (i == 3) {
+            if (i == PPC - 1) {
               umma_commit(smem_u32(&S.acc_bar[buf]));
               if (c == NCHUNK - 1) umma_commit(smem_u32(&S.tile_bar));
             }
@@ -352,8 +404,10 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           g++;
         }
         // front layers of the NEXT tile run in the shadow of this tile's L3 stream
-        if (has_next && c == 2 && has_l1) {
+        if (has_next && c == 1 && has_l1) {
+          tw = clock64();
           mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
+          t_x12 += clock64() - tw;
           tc_fence_after();
           if (elect_one()) {
             issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
@@ -361,8 +415,10 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           }
           __syncwarp();
         }
-        if (has_next && c == 4) {
+        if (has_next && c == (has_l1 ? 3 : 1)) {
+          tw = clock64();
           mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
+          t_x12 += clock64() - tw;
           tc_fence_after();
           if (elect_one()) {
             issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
@@ -371,6 +427,10 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           __syncwarp();
         }
       }
+    }
+    if (a.dbg && lane == 0) {
+      unsigned long long *dd = a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_full; dd[3] = t_accf; dd[4] = t_x12; dd[5] = my_tiles;
     }
   } else if (warp >= NFRONT) {
     // ======================= max warps: L3 epilogue, thread = output channel =======================
@@ -413,98 +473,116 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     const int p = tid & 127, half = tid >> 7;
     const int q = warp & 3;                         // TMEM lane quadrant of this warp
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    for (int it = 0; it < my_tiles; it++) {
-      const int tile = tile_begin + it;
-      // ---------------- input rows + 6 -> 64 on the FMA pipe ----------------
-      {
-        int n = tile * TP + p;
-        if (n >= N) n = N - 1;   // duplicate a valid point: cannot change a max
-        float v[6];
-        if (a.in.x_direct) {
-          const float *xr = a.in.x_direct + ((size_t)b * N + n) * 6;
+    // raw input row of this thread's point for the tile being prepared (prefetched one tile ahead so that the
+    // dependent global loads ids -> cloud row are off the critical path between two tiles)
+    double rx[6];
+    float rv[6];
+    auto prefetch = [&](int tile) {
+      int n = tile * TP + p;
+      if (n >= N) n = N - 1;   // duplicate a valid point: cannot change a max
+      if (a.in.x_direct) {
+        const float *xr = a.in.x_direct + ((size_t)b * N + n) * 6;
 #pragma unroll
-          for (int k = 0; k < 6; k++) v[k] = xr[k];
-        } else {
-          const int id = a.in.ids ? a.in.ids[(size_t)b * N + n] : n;
-          const double *px = a.in.cloud_xyz + (size_t)id * 3;
-          const double *pn = a.in.cloud_nrm + (size_t)id * 3;
-          const double x = px[0], y = px[1], z = px[2];
-          const double nx = pn[0], ny = pn[1], nz = pn[2];
-          const double *R = S.pinv;
-          double w[6];
-          w[0] = R[0] * x + R[1] * y + R[2] * z + R[9];
-          w[1] = R[3] * x + R[4] * y + R[5] * z + R[10];
-          w[2] = R[6] * x + R[7] * y + R[8] * z + R[11];
-          w[3] = R[0] * nx + R[1] * ny + R[2] * nz;
-          w[4] = R[3] * nx + R[4] * ny + R[5] * nz;
-          w[5] = R[6] * nx + R[7] * ny + R[8] * nz;
+        for (int k = 0; k < 6; k++) rv[k] = xr[k];
+      } else {
+        const int id = a.in.ids ? a.in.ids[(size_t)b * N + n] : n;
+        const double *px = a.in.cloud_xyz + (size_t)id * 3;
+        const double *pn = a.in.cloud_nrm + (size_t)id * 3;
+        rx[0] = px[0]; rx[1] = px[1]; rx[2] = px[2]; rx[3] = pn[0]; rx[4] = pn[1]; rx[5] = pn[2];
+      }
+    };
+    // 6 -> 64 (+bias, ReLU) of the prefetched row -> this thread's 32-channel slice of the XA tile
+    auto layer0 = [&]() {
+      float v[6];
+      if (a.in.x_direct) {
 #pragma unroll
-          for (int k = 0; k < 6; k++) v[k] = (float)((w[k] - S.mean[k]) / S.sden[k]);
+        for (int k = 0; k < 6; k++) v[k] = rv[k];
+      } else {
+        const double x = rx[0], y = rx[1], z = rx[2];
+        const double nx = rx[3], ny = rx[4], nz = rx[5];
+        const double *R = S.pinv;
+        double w[6];
+        w[0] = R[0] * x + R[1] * y + R[2] * z + R[9];
+        w[1] = R[3] * x + R[4] * y + R[5] * z + R[10];
+        w[2] = R[6] * x + R[7] * y + R[8] * z + R[11];
+        w[3] = R[0] * nx + R[1] * ny + R[2] * nz;
+        w[4] = R[3] * nx + R[4] * ny + R[5] * nz;
+        w[5] = R[6] * nx + R[7] * ny + R[8] * nz;
+#pragma unroll
+        for (int k = 0; k < 6; k++) v[k] = (float)((w[k] - S.mean[k]) * S.sden[k]);
+      }
+      if (a.T3) {  // xyz @ T3 (pointnet2.py:248), normals pass through (:245-250)
+        const float x = v[0], y = v[1], z = v[2];
+        v[0] = fmaf(z, S.T3[6], fmaf(y, S.T3[3], x * S.T3[0]));
+        v[1] = fmaf(z, S.T3[7], fmaf(y, S.T3[4], x * S.T3[1]));
+        v[2] = fmaf(z, S.T3[8], fmaf(y, S.T3[5], x * S.T3[2]));
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        const int c0 = half * 32 + cc * 8;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+          const float4 wa = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0]);
+          const float4 wb = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0 + 4]);
+          o[0] = fmaf(v[k], wa.x, o[0]); o[1] = fmaf(v[k], wa.y, o[1]); o[2] = fmaf(v[k], wa.z, o[2]); o[3] = fmaf(v[k], wa.w, o[3]);
+          o[4] = fmaf(v[k], wb.x, o[4]); o[5] = fmaf(v[k], wb.y, o[5]); o[6] = fmaf(v[k], wb.z, o[6]); o[7] = fmaf(v[k], wb.w, o[7]);
         }
-        if (a.T3) {  // xyz @ T3 (pointnet2.py:248), normals pass through (:245-250)
-          const float x = v[0], y = v[1], z = v[2];
-          v[0] = fmaf(z, S.T3[6], fmaf(y, S.T3[3], x * S.T3[0]));
-          v[1] = fmaf(z, S.T3[7], fmaf(y, S.T3[4], x * S.T3[1]));
-          v[2] = fmaf(z, S.T3[8], fmaf(y, S.T3[5], x * S.T3[2]));
-        }
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-          const int c0 = half * 32 + cc * 8;
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) o[j] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 6; k++) {
-            const float4 wa = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0]);
-            const float4 wb = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0 + 4]);
-            o[0] = fmaf(v[k], wa.x, o[0]); o[1] = fmaf(v[k], wa.y, o[1]); o[2] = fmaf(v[k], wa.z, o[2]); o[3] = fmaf(v[k], wa.w, o[3]);
-            o[4] = fmaf(v[k], wb.x, o[4]); o[5] = fmaf(v[k], wb.y, o[5]); o[6] = fmaf(v[k], wb.z, o[6]); o[7] = fmaf(v[k], wb.w, o[7]);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j] + S.bias0[c0 + j], 0.f);
-          const uint32_t off = row_chunk_off(p, c0 >> 3);
-          store_hilo8(xa + off, xa + PIECE + off, o);
-        }
+        for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j] + S.bias0[c0 + j], 0.f);
+        const uint32_t off = row_chunk_off(p, c0 >> 3);
+        store_hilo8(xa + off, xa + PIECE + off, o);
       }
       fence_proxy_async();   // generic-proxy tile writes -> visible to the async proxy (UMMA operand reads)
       bar_front();
-      if (tid == 0) mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
-
-      // ---------------- L1 epilogue: D1 -> (bias, ReLU | nothing) -> XA as the L2 input ----------------
-      if (has_l1) {
-        mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
-        tc_fence_after();
-        {
-          float v[32];
-          tmem_ld32(tmem_base + lane_sel + D1_COL + (uint32_t)half * 32u, v);
-          if (a.stage1_mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias1[half * 32 + j], 0.f);
-          }
-          if (a.pf_out) {   // PointNetSeg point feature (pointnet2.py:261)
-            const int n = tile * TP + p;
-            if (n < N) {
-              float4 *dstg = reinterpret_cast<float4 *>(a.pf_out + ((size_t)b * N + n) * 64 + half * 32);
-#pragma unroll
-              for (int j = 0; j < 8; j++) dstg[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-          }
-#pragma unroll
-          for (int cc = 0; cc < 4; cc++) {
-            const uint32_t off = row_chunk_off(p, half * 4 + cc);
-            store_hilo8(xa + off, xa + PIECE + off, v + cc * 8);
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        bar_front();
-        if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
-      }
-
-      // ---------------- L2 epilogue: D2 -> bias, ReLU -> X3 (once the previous tile's L3 has let go of it) -------
-      mbar_wait(smem_u32(&S.l2_bar), (uint32_t)it & 1u);
-      if (it >= 1) mbar_wait(smem_u32(&S.tile_bar), (uint32_t)(it - 1) & 1u);
+    };
+    // L1 epilogue of tile `tile` (local index it): D1 -> (bias, ReLU | nothing) -> XA as the L2 input
+    auto l1_epilogue = [&](int tile, int it) {
+      mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
       tc_fence_after();
+      float v[32];
+      tmem_ld32(tmem_base + lane_sel + D1_COL + (uint32_t)half * 32u, v);
+      if (a.stage1_mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias1[half * 32 + j], 0.f);
+      }
+      if (a.pf_out) {   // PointNetSeg point feature (pointnet2.py:261)
+        const int n = tile * TP + p;
+        if (n < N) {
+          float4 *dstg = reinterpret_cast<float4 *>(a.pf_out + ((size_t)b * N + n) * 64 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; j++) dstg[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {
+        const uint32_t off = row_chunk_off(p, half * 4 + cc);
+        store_hilo8(xa + off, xa + PIECE + off, v + cc * 8);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      bar_front();
+      if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
+    };
+
+    // ---- prologue: front layers of the first tile ----
+    prefetch(tile_begin);
+    layer0();
+    if (tid == 0) mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
+    if (my_tiles > 1) prefetch(tile_begin + 1);
+    if (has_l1) l1_epilogue(tile_begin, 0);
+
+    for (int it = 0; it < my_tiles; it++) {
+      const int tile = tile_begin + it;
+      const bool has_next = it + 1 < my_tiles;
+      // A. D2(tile) complete; its UMMAs no longer read XA
+      mbar_wait(smem_u32(&S.l2_bar), (uint32_t)it & 1u);
+      tc_fence_after();
+      // C. L2 epilogue: D2 -> bias, ReLU -> packed hi/lo in registers; the X3 stores wait until the previous tile's
+      //    L3 has let go of X3, so only 16 x st.shared.v4 sit between two tiles' L3 streams
+      uint32_t ph[2][4][4], pl[2][4][4];
 #pragma unroll
       for (int j32 = 0; j32 < 2; j32++) {
         float v[32];
@@ -512,16 +590,30 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias2[half * 64 + j32 * 32 + j], 0.f);
 #pragma unroll
+        for (int cc = 0; cc < 4; cc++) pack_hilo8<PASSES == 2>(v + cc * 8, ph[j32][cc], pl[j32][cc]);
+      }
+      if (it >= 1) mbar_wait(smem_u32(&S.tile_bar), (uint32_t)(it - 1) & 1u);
+#pragma unroll
+      for (int j32 = 0; j32 < 2; j32++)
+#pragma unroll
         for (int cc = 0; cc < 4; cc++) {
           // channel = half*64 + j32*32 + cc*8 ..  ->  K-block `half`, 16-byte chunk j32*4 + cc
           const uint32_t off = (uint32_t)half * PIECE + row_chunk_off(p, j32 * 4 + cc);
-          store_hilo8(x3 + off, x3 + 2 * PIECE + off, v + cc * 8);
+          *reinterpret_cast<uint4 *>(x3 + off) = make_uint4(ph[j32][cc][0], ph[j32][cc][1], ph[j32][cc][2], ph[j32][cc][3]);
+          *reinterpret_cast<uint4 *>(x3 + 2 * PIECE + off) = make_uint4(pl[j32][cc][0], pl[j32][cc][1], pl[j32][cc][2], pl[j32][cc][3]);
         }
-      }
       tc_fence_before();
       fence_proxy_async();
       bar_front();
       if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
+      // B. 6 -> 64 of the NEXT tile (inputs were prefetched a tile ago)
+      if (has_next) {
+        layer0();
+        if (tid == 0) mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
+        if (it + 2 < my_tiles) prefetch(tile + 2);   // loads stay in flight across the waits below
+      }
+      // D. L1 epilogue of the next tile
+      if (has_next && has_l1) l1_epilogue(tile + 1, it + 1);
     }
   }
 
@@ -563,7 +655,7 @@ void pack_image(const float *Wt, int C, int c0, int rows, int nkb, unsigned char
 
 }  // namespace
 
-size_t cg_tc_image_bytes() { return (size_t)W3_IMG + W2_IMG + W1_IMG; }
+size_t cg_tc_image_bytes() { return (size_t)W3_IMG + W2_IMG + W1_IMG + W3H_IMG; }
 
 int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *Wt1, void *dst_dev) {
   std::vector<unsigned char> img(cg_tc_image_bytes(), 0);
@@ -571,6 +663,17 @@ int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *
   for (int ch = 0; ch < NCHUNK; ch++) pack_image(Wt3, 1024, ch * 128, 128, 2, img.data() + (size_t)ch * 4 * PIECE);
   pack_image(Wt2, 128, 0, 128, 1, img.data() + W3_IMG);            // [hi 16 KB][lo 16 KB]
   if (Wt1) pack_image(Wt1, 64, 0, 64, 1, img.data() + W3_IMG + W2_IMG);   // [hi 8 KB][lo 8 KB]
+  // fp16 single-term W3 for the 2-pass engine: per chunk [kb0 16 KB][kb1 16 KB]
+  for (int ch = 0; ch < NCHUNK; ch++)
+    for (int r = 0; r < 128; r++)
+      for (int k = 0; k < 128; k++) {
+        const __half h = __float2half_rn(Wt3[(size_t)k * 1024 + ch * 128 + r]);
+        unsigned short bits;
+        memcpy(&bits, &h, 2);
+        const size_t off = (size_t)W3H_OFF + (size_t)ch * 2 * PIECE + (size_t)(k >> 6) * PIECE + row_chunk_off(r, (k & 63) >> 3) +
+                           (size_t)(k & 7) * 2;
+        memcpy(img.data() + off, &bits, 2);
+      }
   CG_CUDA(ctx, cudaMemcpyAsync(dst_dev, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
   CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // img goes out of scope
   return CG_OK;
@@ -582,7 +685,8 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_REQUIRE(ctx, a.tc_img != nullptr, "trunk: tensor-core weight image missing");
   static bool attr_set = false;
   if (!attr_set) {
-    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set = true;
   }
   const int ntiles = (a.N + TP - 1) / TP;
@@ -590,6 +694,7 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   while ((long)a.B * splits < 4L * ctx->num_sms && splits < ntiles) splits *= 2;
   const int tiles_per_cta = (ntiles + splits - 1) / splits;
   dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, a.B);
+  const bool two_pass = ctx->engine == 2;
   static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
   if (debug) {
     cg_trunk_args ad = a;
@@ -598,7 +703,8 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
     CG_CUDA(ctx, cudaMalloc(&d_dbg, n * 64));
     CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n * 64, ctx->stream));
     ad.dbg = d_dbg;
-    trunk_tc_kernel<<<grid, NTC, SMEM_BYTES, ctx->stream>>>(ad, tiles_per_cta);
+    if (two_pass) trunk_tc_kernel<2><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(ad, tiles_per_cta);
+    else trunk_tc_kernel<3><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(ad, tiles_per_cta);
     CG_LAUNCH_CHECK(ctx);
     std::vector<unsigned long long> h(n * 8);
     CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -612,7 +718,8 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
             n, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles, s[3] / tiles);
     return CG_OK;
   }
-  trunk_tc_kernel<<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
+  if (two_pass) trunk_tc_kernel<2><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
+  else trunk_tc_kernel<3><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
   CG_LAUNCH_CHECK(ctx);
   return CG_OK;
 }

@@ -13,7 +13,7 @@ for (B, N) in [(1, 128), (2, 300), (4, 1024), (64, 1024)]:
     x = rng.normal(0, 1, (B, N, 6)).astype(np.float32)
     ref = pointnet_cls_forward(sd, x)[0]
     out = {}
-    for e in (0, 1):
+    for e in (0, 1, 2):
         net.ctx.set_engine(e)
         t = time.time()
         lg, pr = net.forward(x, return_probs=True)
@@ -21,4 +21,5 @@ for (B, N) in [(1, 128), (2, 300), (4, 1024), (64, 1024)]:
         out[e] = (lg.cpu().numpy(), pr.cpu().numpy(), time.time() - t)
     print(f"B={B} N={N}: e0 vs ref dlogit {np.abs(out[0][0]-ref.numpy()).max():.2e}  "
           f"e1 vs ref dlogit {np.abs(out[1][0]-ref.numpy()).max():.2e} dprob {np.abs(out[1][1]-ref.softmax(1).numpy()).max():.2e}  "
-          f"e1 vs e0 dlogit {np.abs(out[1][0]-out[0][0]).max():.2e}  t0={out[0][2]*1e3:.1f}ms t1={out[1][2]*1e3:.1f}ms", flush=True)
+          f"e2 vs ref dlogit {np.abs(out[2][0]-ref.numpy()).max():.2e} dprob {np.abs(out[2][1]-ref.softmax(1).numpy()).max():.2e}  "
+          f"t0={out[0][2]*1e3:.1f}ms t1={out[1][2]*1e3:.1f}ms t2={out[2][2]*1e3:.1f}ms", flush=True)
