@@ -22,6 +22,7 @@ struct cg_sdf {
   int nx, ny, nz;
   float origin[3];
   float res;
+  int border_nonneg;   // every cell on the six boundary faces is >= 0 (true for padded grids, make_sdf.py:30)
 };
 
 namespace {
@@ -31,6 +32,7 @@ struct SdfView {
   int nx, ny, nz;
   float ox, oy, oz;
   float inv_res;
+  int border_nonneg;
 };
 
 __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -142,7 +144,15 @@ __device__ __forceinline__ bool point_hits(const SdfView &s, const float *inv, i
   const float gx = mul(sub(qx, s.ox), s.inv_res);   // sdf.py:252-264
   const float gy = mul(sub(qy, s.oy), s.inv_res);
   const float gz = mul(sub(qz, s.oz), s.inv_res);
-  if (mode == CG_SDF_TRILINEAR) return sdf_trilinear(s, gx, gy, gz) < 0.f;
+  if (mode == CG_SDF_TRILINEAR) {
+    // Exact shortcut: a coordinate outside [0, dim-1] is clamped onto a boundary face (sdf.py:311-313) and then
+    // interpolates boundary cells only; when all of those are >= 0 the result cannot be < 0, so the eight gathers
+    // are skipped.  Most scene points are far from the gripper box, which makes this the common path.
+    if (s.border_nonneg && (gx < 0.f || gy < 0.f || gz < 0.f || gx > (float)(s.nx - 1) || gy > (float)(s.ny - 1) ||
+                            gz > (float)(s.nz - 1)))
+      return false;
+    return sdf_trilinear(s, gx, gy, gz) < 0.f;
+  }
   bool inb;
   const float sd = sdf_nearest(s, gx, gy, gz, false, &inb);
   return inb && (sd < 0.f);
@@ -251,6 +261,7 @@ SdfView make_view(const cg_sdf *s) {
   v.grid = s->grid; v.nx = s->nx; v.ny = s->ny; v.nz = s->nz;
   v.ox = s->origin[0]; v.oy = s->origin[1]; v.oz = s->origin[2];
   v.inv_res = 1.0f / s->res;
+  v.border_nonneg = s->border_nonneg;
   return v;
 }
 
@@ -265,6 +276,13 @@ extern "C" int cg_sdf_create(cg_ctx *ctx, const float *grid_host, int nx, int ny
   s->ctx = ctx; s->nx = nx; s->ny = ny; s->nz = nz; s->res = resolution;
   for (int k = 0; k < 3; k++) s->origin[k] = origin[k];
   const size_t bytes = (size_t)nx * ny * nz * sizeof(float);
+  s->border_nonneg = 1;
+  for (int i = 0; i < nx && s->border_nonneg; i++)
+    for (int j = 0; j < ny && s->border_nonneg; j++)
+      for (int k = 0; k < nz; k++) {
+        if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1) { k = nz - 2; continue; }   // jump to the far face
+        if (!(grid_host[((size_t)i * ny + j) * nz + k] >= 0.f)) { s->border_nonneg = 0; break; }
+      }
   CG_CUDA(ctx, cudaMalloc(&s->grid, bytes));
   CG_CUDA(ctx, cudaMemcpyAsync(s->grid, grid_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

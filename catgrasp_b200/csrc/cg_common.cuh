@@ -19,7 +19,7 @@ struct cg_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
-  int engine = 1;  // 0 = fp32 SIMT, 1 = tcgen05 (default)
+  int engine = 2;  // 0 = fp32 SIMT, 1 = tcgen05 bf16 3-pass, 2 = tcgen05 fp16 2-pass (default)
   int num_sms = 148;
   // optional event-pair timing of trunk launches (bench roofline)
   bool prof = false;

@@ -179,6 +179,66 @@ __global__ void __launch_bounds__(256) linear_wide_kernel(const float *__restric
   }
 }
 
+
+// Few-row variant (M <= 8: the per-scene NUNOCS heads, B = 1): 64 output columns per CTA, K split over 16 thread
+// groups whose partial sums meet in shared memory -- latency-bound GEMV work that the tiled kernels serialise badly.
+constexpr int RM = 8;
+
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float *__restrict__ X, int M, int K,
+                                                           const float *__restrict__ Wt,
+                                                           const float *__restrict__ bias, int N, int relu,
+                                                           int bias_row_div, int x_is_keys,
+                                                           float *__restrict__ Y) {
+  __shared__ float red[16][RM][64 + 1];
+  const int tid = threadIdx.x;
+  const int nq = tid & 15, ks = tid >> 4;          // 16 column quads x 16 k-slices
+  const int n = blockIdx.x * 64 + nq * 4;
+  float acc[RM][4];
+#pragma unroll
+  for (int m = 0; m < RM; m++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[m][j] = 0.f;
+  const int kper = (K + 15) / 16;
+  const int k0 = ks * kper, k1 = min(K, k0 + kper);
+  const bool vec = ((N & 3) == 0) && (n + 4 <= N);
+#pragma unroll 4
+  for (int k = k0; k < k1; k++) {
+    float w[4];
+    if (vec) {
+      const float4 t = *reinterpret_cast<const float4 *>(Wt + (size_t)k * N + n);
+      w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) w[j] = (n + j < N) ? Wt[(size_t)k * N + n + j] : 0.f;
+    }
+#pragma unroll
+    for (int m = 0; m < RM; m++) {
+      if (m < M) {
+        float x = X[(size_t)m * K + k];
+        if (x_is_keys) x = cg_key2f(__float_as_uint(x));
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[m][j] = fmaf(x, w[j], acc[m][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < RM; m++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) red[ks][m][nq * 4 + j] = acc[m][j];
+  __syncthreads();
+  for (int o = tid; o < M * 64; o += 256) {
+    const int m = o >> 6, c = o & 63;
+    const int col = blockIdx.x * 64 + c;
+    if (col >= N) continue;
+    float v = 0.f;
+#pragma unroll
+    for (int s2 = 0; s2 < 16; s2++) v += red[s2][m][c];
+    if (bias) v += bias[(size_t)(bias_row_div > 0 ? (m / bias_row_div) : 0) * N + col];
+    if (relu) v = fmaxf(v, 0.f);
+    Y[(size_t)m * N + col] = v;
+  }
+}
+
 // softmax over C <= 32 classes, one warp per row (predicter.py:86-90)
 __global__ void softmax_kernel(const float *__restrict__ logits, int B, int C, float *__restrict__ probs,
                                int32_t *__restrict__ label) {
@@ -242,6 +302,11 @@ __global__ void nunocs_post_kernel(const float *__restrict__ logits, int P, int 
 int cg_linear_launch(cg_ctx *ctx, const float *X, int M, int K, const float *Wt, const float *bias, int N,
                      int relu, int bias_row_div, int x_is_keys, float *Y) {
   CG_REQUIRE(ctx, M > 0 && K > 0 && N > 0, "linear: bad shape");
+  if (M <= RM) {
+    linear_rows_kernel<<<(N + 63) / 64, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
+    CG_LAUNCH_CHECK(ctx);
+    return CG_OK;
+  }
   const long wide_ctas = (long)((N + LN - 1) / LN) * ((M + LM - 1) / LM);
   if (N >= 128 && (K % LK) == 0 && (K % 4) == 0 && wide_ctas >= ctx->num_sms) {
     dim3 gridw((N + LN - 1) / LN, (M + LM - 1) / LM);

@@ -77,7 +77,7 @@ extern "C" int cg_net_create(cg_ctx *ctx, int kind, int n_out, const float *blob
   for (int i = 0; i < 3; i++) {
     CG_CUDA(ctx, cudaMalloc(&net->tc_img[i], cg_tc_image_bytes()));
     int rc = cg_tc_prepare(ctx, blob_host + woff[l3[i]], blob_host + woff[l2[i]],
-                           l1[i] >= 0 ? blob_host + woff[l1[i]] : nullptr, net->tc_img[i]);
+                           l1[i] >= 0 ? blob_host + woff[l1[i]] : nullptr, net->tc_img[i], &net->tc_f16_ok[i]);
     if (rc != CG_OK) return rc;
   }
   CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -143,7 +143,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   // --- trunk A: STN3d convs + max (pointnet2.py:170-175)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.T3 = nullptr; a.l0 = L[L_S3_C1]; a.stage1_mode = 0; a.l1 = cg_layer{nullptr, nullptr, 0, 0}; a.T64 = nullptr;
-  a.l2 = L[L_S3_C2]; a.l3 = L[L_S3_C3]; a.tc_img = net->tc_img[0]; a.relu3 = 1; a.gmax_keys = w.gmax; a.pf_out = nullptr;
+  a.l2 = L[L_S3_C2]; a.l3 = L[L_S3_C3]; a.tc_img = net->tc_img[0]; a.tc_f16_ok = net->tc_f16_ok[0]; a.relu3 = 1; a.gmax_keys = w.gmax; a.pf_out = nullptr;
   if ((rc = trunk_launch(ctx, a))) return rc;
   if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_S3_F1].Wt, L[L_S3_F1].b, 512, 1, 0, 1, w.f1))) return rc;
   if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_S3_F2].Wt, L[L_S3_F2].b, 256, 1, 0, 0, w.f2))) return rc;
@@ -151,7 +151,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   // --- trunk B: encoder conv1 + STNkd convs + max (pointnet2.py:252, :208-213)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.T3 = w.T3; a.l0 = L[L_E_C1]; a.stage1_mode = 1; a.l1 = L[L_SK_C1];
-  a.l2 = L[L_SK_C2]; a.l3 = L[L_SK_C3]; a.tc_img = net->tc_img[1]; a.relu3 = 1;
+  a.l2 = L[L_SK_C2]; a.l3 = L[L_SK_C3]; a.tc_img = net->tc_img[1]; a.tc_f16_ok = net->tc_f16_ok[1]; a.relu3 = 1;
   if ((rc = trunk_launch(ctx, a))) return rc;
   if ((rc = cg_linear_launch(ctx, reinterpret_cast<float *>(w.gmax), B, 1024, L[L_SK_F1].Wt, L[L_SK_F1].b, 512, 1, 0, 1, w.f1))) return rc;
   if ((rc = cg_linear_launch(ctx, w.f1, B, 512, L[L_SK_F2].Wt, L[L_SK_F2].b, 256, 1, 0, 0, w.f2))) return rc;
@@ -159,7 +159,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   // --- trunk C: conv1, @T64, conv2, conv3(+BN, no ReLU), max (pointnet2.py:252-265)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.stage1_mode = 2; a.T64 = w.T64; a.l1 = cg_layer{nullptr, nullptr, 64, 64};
-  a.l2 = L[L_E_C2]; a.l3 = L[L_E_C3]; a.tc_img = net->tc_img[2]; a.relu3 = 0; a.pf_out = pf_out;
+  a.l2 = L[L_E_C2]; a.l3 = L[L_E_C3]; a.tc_img = net->tc_img[2]; a.tc_f16_ok = net->tc_f16_ok[2]; a.relu3 = 0; a.pf_out = pf_out;
   if ((rc = trunk_launch(ctx, a))) return rc;
   return CG_OK;
 }

@@ -657,7 +657,10 @@ void pack_image(const float *Wt, int C, int c0, int rows, int nkb, unsigned char
 
 size_t cg_tc_image_bytes() { return (size_t)W3_IMG + W2_IMG + W1_IMG + W3H_IMG; }
 
-int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *Wt1, void *dst_dev) {
+int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *Wt1, void *dst_dev, int *f16_ok) {
+  float wmax = 0.f;
+  for (size_t i = 0; i < (size_t)128 * 1024; i++) wmax = fmaxf(wmax, fabsf(Wt3[i]));
+  *f16_ok = (wmax < 65504.f) ? 1 : 0;   // otherwise the fp16 image would hold infinities
   std::vector<unsigned char> img(cg_tc_image_bytes(), 0);
   // W3: per 128-channel chunk one 64 KB tile whose four 16 KB pieces are [hi kb0][hi kb1][lo kb0][lo kb1]
   for (int ch = 0; ch < NCHUNK; ch++) pack_image(Wt3, 1024, ch * 128, 128, 2, img.data() + (size_t)ch * 4 * PIECE);
@@ -694,7 +697,7 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   while ((long)a.B * splits < 4L * ctx->num_sms && splits < ntiles) splits *= 2;
   const int tiles_per_cta = (ntiles + splits - 1) / splits;
   dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, a.B);
-  const bool two_pass = ctx->engine == 2;
+  const bool two_pass = ctx->engine == 2 && a.tc_f16_ok;
   static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
   if (debug) {
     cg_trunk_args ad = a;

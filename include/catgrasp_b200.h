@@ -54,8 +54,10 @@ int64_t     cg_ctx_launch_count(cg_ctx *ctx);
 void        cg_ctx_reset_launch_count(cg_ctx *ctx);
 /* GEMM engine of the fused shared-MLP "trunk":
  *   0 = fp32 SIMT (exact-order reference engine)
- *   1 = tcgen05, bf16 hi/lo x hi/lo, 3 passes (near-fp32: |dprob| ~ 1e-7)     [default]
- *   2 = tcgen05, 128->1024 weights as one fp16 term, 2 passes (|dprob| ~ 5e-6)  */
+ *   1 = tcgen05, bf16 hi/lo x hi/lo, 3 passes (near-fp32: |dprob| ~ 1e-7)
+ *   2 = tcgen05, 128->1024 layer with fp16 hi/lo activations x one fp16 weight
+ *       term, 2 passes (|dprob| ~ 2e-6 vs the 1e-4 tolerance)               [default]
+ *       (falls back to 1 for a net whose folded weights exceed the fp16 range) */
 int         cg_ctx_set_engine(cg_ctx *ctx, int engine);
 int         cg_ctx_get_engine(cg_ctx *ctx);
 /* Optional in-stream timing of the dominant kernel (the fused shared-MLP+max

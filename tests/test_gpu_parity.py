@@ -25,7 +25,7 @@ def cuda():
 
 
 def _engines():
-    return [int(e) for e in os.environ.get("CG_TEST_ENGINES", "0,1").split(",")]
+    return [int(e) for e in os.environ.get("CG_TEST_ENGINES", "0,1,2").split(",")]
 
 
 @pytest.fixture(scope="module")
@@ -51,7 +51,7 @@ def test_cls_vs_reference_golden(cls_net, golden_dir, engine):
     net.ctx.set_engine(engine)
     g = np.load(os.path.join(golden_dir, "pointnet_cls.npz"))
     logits, probs = net.forward(g["x"], return_probs=True)
-    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < LOGIT_TOL
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() < LOGIT_TOL * (1 if engine < 2 else 4)
     assert np.abs(probs.cpu().numpy() - g["probs"]).max() < PROB_TOL
 
 
@@ -61,7 +61,7 @@ def test_seg_vs_reference_golden(seg_net, golden_dir, engine):
     net.ctx.set_engine(engine)
     g = np.load(os.path.join(golden_dir, "pointnet_seg.npz"))
     logits = net.forward(g["x"]).cpu().numpy()
-    assert np.abs(logits - g["logits"]).max() < (2e-3 if engine == 1 else 2e-4)
+    assert np.abs(logits - g["logits"]).max() < (2e-4 if engine < 2 else 2e-3)
 
 
 @pytest.mark.parametrize("engine", _engines())
@@ -75,7 +75,7 @@ def test_cls_ragged_shapes_vs_oracle(cls_net, engine, B, N):
     ref = pointnet_cls_forward(sd, x)[0]
     logits, probs = net.forward(x, return_probs=True)
     assert np.abs(probs.cpu().numpy() - ref.softmax(1).numpy()).max() < PROB_TOL
-    assert np.abs(logits.cpu().numpy() - ref.numpy()).max() < LOGIT_TOL * (4 if engine == 1 else 1)
+    assert np.abs(logits.cpu().numpy() - ref.numpy()).max() < LOGIT_TOL * (4 if engine == 2 else 1)
 
 
 @pytest.mark.parametrize("engine", _engines())
