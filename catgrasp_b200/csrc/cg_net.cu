@@ -139,7 +139,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   const cg_layer *L = net->L;
   int rc;
   cg_trunk_args a;
-  a.in = in; a.B = B; a.N = N; a.dbg = nullptr;
+  a.in = in; a.B = B; a.N = N; a.dbg = nullptr; a.exp_flags = 0;
   // --- trunk A: STN3d convs + max (pointnet2.py:170-175)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.T3 = nullptr; a.l0 = L[L_S3_C1]; a.stage1_mode = 0; a.l1 = cg_layer{nullptr, nullptr, 0, 0}; a.T64 = nullptr;

@@ -59,6 +59,8 @@ struct cg_trunk_args {
   uint32_t *gmax_keys;  // (B,1024) order-preserving keys, zero-initialised by the launcher
   float *pf_out;        // (B,N,64) stage-1 output (PointNetSeg point feature) or nullptr
   unsigned long long *dbg;  // optional per-CTA cycle counters (CG_TRUNK_DEBUG=1), else nullptr
+  int exp_flags;            // timing experiments only (CG_TRUNK_EXP bitmask, results become wrong): 1 = no W3 copies,
+                            // 2 = max warps skip the TMEM reads, 4 = front warps skip their math
 };
 
 int cg_trunk_launch_simt(cg_ctx *ctx, const cg_trunk_args &a);

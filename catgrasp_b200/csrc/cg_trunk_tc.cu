@@ -40,21 +40,30 @@ constexpr int MMA_WARP = PROD_WARP + 1;    // warp 13: UMMA issuer
 constexpr int NTC = (MMA_WARP + 1) * 32;   // 448 threads
 constexpr int NFT = NFRONT * 32;           // 256 front threads
 constexpr uint32_t PIECE = 16384;          // [128 rows x 64 bf16] one swizzled K-block
-constexpr uint32_t X3_OFF = 0;             // [hi|lo][kb0|kb1] 64 KB  L3 input tile
-constexpr uint32_t XA_OFF = 4 * PIECE;     // [hi|lo] 32 KB: X1 (L1 input), then X2 (L2 input) of the same tile
-constexpr uint32_t W1_OFF = 6 * PIECE;     // [hi|lo][64 rows x 128 B] 16 KB
-constexpr uint32_t W2_OFF = 7 * PIECE;     // [hi|lo][128 rows x 128 B] 32 KB
-constexpr uint32_t RING_OFF = 9 * PIECE;   // 4 x 16 KB pieces of W3
-constexpr int NSLOT = 4;
-constexpr uint32_t MISC_OFF = RING_OFF + NSLOT * PIECE;   // 208 KB
+// Shared-memory map (multiples of the 16 KB piece).  TS = false: the L3 input tile X3 lives in shared memory
+// (SS-mode UMMA) and the W3 ring has 4 slots.  TS = true: X3 lives in TMEM as the A operand (TS-mode UMMA), which
+// halves the L3 operand traffic on the shared-memory port and frees 64 KB for an 8-slot ring.
+constexpr uint32_t XA_OFF = 0;             // [hi|lo] 32 KB: X1 (L1 input), then X2 (L2 input) of the same tile
+constexpr uint32_t W1_OFF = 2 * PIECE;     // [hi|lo][64 rows x 128 B] 16 KB
+constexpr uint32_t W2_OFF = 3 * PIECE;     // [hi|lo][128 rows x 128 B] 32 KB
+constexpr uint32_t X3_OFF = 5 * PIECE;     // SS only: [hi|lo][kb0|kb1] 64 KB
+template <bool TS> struct Lay {
+  static constexpr int NSLOT = TS ? 8 : 4;
+  static constexpr int SLOT_SHIFT = TS ? 3 : 2;
+  static constexpr uint32_t RING_OFF = TS ? 5 * PIECE : 9 * PIECE;
+  static constexpr uint32_t MISC_OFF = 13 * PIECE;          // 208 KB in both variants
+  // TMEM columns: D3 x2 at 0 / 128;  SS: D1 256, D2 320;  TS: D2 256 (D1 aliases it), X3 hi 384, X3 lo 448
+  static constexpr uint32_t D1_COL = 256, D2_COL = TS ? 256 : 320, X3H_COL = 384, X3L_COL = 448;
+};
+constexpr int NSLOT_MAX = 8;
 constexpr int NCHUNK = 8;                  // 1024 output channels / 128
-constexpr uint32_t TMEM_COLS = 512;        // D3 x2 (0..255), D1 (256..319), D2 (320..447)
-constexpr uint32_t D1_COL = 256, D2_COL = 320;
+constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t W3_IMG = NCHUNK * 4 * PIECE, W2_IMG = 2 * PIECE, W1_IMG = PIECE;
 constexpr uint32_t W3H_OFF = W3_IMG + W2_IMG + W1_IMG;   // fp16 single-term image of W3 (2-pass engine)
 constexpr uint32_t W3H_IMG = NCHUNK * 2 * PIECE;
 
 struct Misc {
+  uint32_t gmax_s[1024];   // TS variant: running max per channel (order-preserving keys)
   float w0[6 * 64];
   float bias0[64];
   float bias1[64];
@@ -63,8 +72,8 @@ struct Misc {
   double mean[6];
   double sden[6];
   float T3[12];
-  unsigned long long full_bar[NSLOT];     // producer -> MMA : W3 piece landed in ring slot
-  unsigned long long free_bar[NSLOT];     // MMA -> producer : UMMAs reading the slot have completed
+  unsigned long long full_bar[NSLOT_MAX]; // producer -> MMA : W3 piece landed in ring slot
+  unsigned long long free_bar[NSLOT_MAX];     // MMA -> producer : UMMAs reading the slot have completed
   unsigned long long acc_bar[2];          // MMA -> max      : chunk accumulated into D3[buf]
   unsigned long long accfree_bar[2];      // max -> MMA      : D3[buf] drained (one arrival per max warp)
   unsigned long long x1_bar, x2_bar, x3_bar;   // front -> MMA : XA holds X1 / XA holds X2 / X3 written
@@ -74,7 +83,7 @@ struct Misc {
   uint32_t tmem_base;
 };
 
-constexpr size_t SMEM_BYTES = MISC_OFF + sizeof(Misc) + 1024;  // + slack for manual 1024-byte alignment
+constexpr size_t SMEM_BYTES = 13 * PIECE + sizeof(Misc) + 1024;  // + slack for manual 1024-byte alignment
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -139,6 +148,45 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// TS mode: A operand read from TMEM (lane = M row, 32-bit column = two consecutive K elements), B from shared memory
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t id, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(id), "r"(accumulate)
+      : "memory");
+}
+// 32 registers per thread -> 32 lanes x 32 consecutive 32-bit TMEM columns (thread t <-> lane base + t)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Column-wise max over the 32 lanes of a warp for 32 columns at once: after the five exchange rounds thread t holds
+// max over lanes of column t (31 shuffles instead of 5 x 32).
+__device__ __forceinline__ float warp_colmax32(float *v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      const float keep = up ? v[i + off] : v[i];
+      const float send = up ? v[i] : v[i + off];
+      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -235,13 +283,16 @@ __device__ __forceinline__ void issue_k64(uint32_t d, uint32_t x_s, uint32_t x_p
 
 // PASSES = 3: W3 = bf16 hi + lo, products lo*hi + hi*lo + hi*hi (near-fp32).
 // PASSES = 2: W3 = one fp16 term (11-bit mantissa, rounding error 2^-12 per weight), X3 = fp16 hi + lo.
-template <int PASSES>
+template <int PASSES, bool TS>
 __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a, int tiles_per_cta) {
   constexpr int PPC = (PASSES == 3) ? 4 : 2;   // W3 ring pieces per 128-channel chunk
+  using L = Lay<TS>;
+  constexpr int NSLOT = L::NSLOT;
+  constexpr uint32_t D1_COL = L::D1_COL, D2_COL = L::D2_COL;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char *x3 = smem + X3_OFF, *xa = smem + XA_OFF, *w1 = smem + W1_OFF;
-  Misc &S = *reinterpret_cast<Misc *>(smem + MISC_OFF);
+  Misc &S = *reinterpret_cast<Misc *>(smem + L::MISC_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y;
   const int N = a.N;
@@ -254,6 +305,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
   const bool has_l1 = a.stage1_mode != 0;
 
   // ---- one-time setup: constants, mbarriers, TMEM, per-candidate T64 operand ---------------------------
+  for (int i = tid; i < 1024; i += NTC) S.gmax_s[i] = 0u;
   for (int i = tid; i < 6 * 64; i += NTC) S.w0[i] = a.l0.Wt[i];
   if (tid < 64) {
     S.bias0[tid] = a.l0.b[tid];
@@ -311,7 +363,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
   const uint32_t x3_s = smem_u32(x3), xa_s = smem_u32(xa), w1_s = smem_u32(w1), w2_s = smem_u32(smem + W2_OFF);
-  const uint32_t ring_s = smem_u32(smem + RING_OFF);
+  const uint32_t ring_s = smem_u32(smem + L::RING_OFF);
 
   if (warp == PROD_WARP) {
     // ======================= producer: stream W3 pieces through the ring =======================
@@ -319,11 +371,14 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     const unsigned char *w3src = img + (PASSES == 3 ? 0u : W3H_OFF);
     for (int g = 0; g < total; g++) {
       const int slot = g & (NSLOT - 1);
-      mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> 2) & 1u) ^ 1u);   // first round passes immediately
+      mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> L::SLOT_SHIFT) & 1u) ^ 1u);   // first round passes immediately
       if (elect_one()) {
         const uint32_t fb = smem_u32(&S.full_bar[slot]);
-        mbar_expect_tx(fb, PIECE);
-        bulk_g2s(ring_s + (uint32_t)slot * PIECE, w3src + (size_t)(g & (NCHUNK * PPC - 1)) * PIECE, PIECE, fb);
+        if ((a.exp_flags & 1) && g >= NSLOT) { mbar_arrive(fb); }
+        else {
+          mbar_expect_tx(fb, PIECE);
+          bulk_g2s(ring_s + (uint32_t)slot * PIECE, w3src + (size_t)(g & (NCHUNK * PPC - 1)) * PIECE, PIECE, fb);
+        }
       }
       __syncwarp();
     }
@@ -377,7 +432,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
         for (int i = 0; i < PPC; i++) {    // 3-pass pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1;  2-pass: W3 kb0, kb1
           const int slot = g & (NSLOT - 1);
           tw = clock64();
-          mbar_wait(smem_u32(&S.full_bar[slot]), (g >> 2) & 1u);
+          mbar_wait(smem_u32(&S.full_bar[slot]), (g >> L::SLOT_SHIFT) & 1u);
           t_full += clock64() - tw;
           tc_fence_after();
           const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
@@ -386,12 +441,22 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
               const uint32_t koff = (uint32_t)ks * 32u;
-              const uint64_t ad = umma_desc(a_s + koff);
-              if (PASSES == 2 || i < 2) {
-                umma(d, ad, umma_desc(x3_s + 2 * PIECE + kb + koff), id, (i | ks) ? 1u : 0u);   // w(_hi) * x_lo
-                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w(_hi) * x_hi
+              const uint64_t wd = umma_desc(a_s + koff);     // W3 piece rows = 128 channels
+              const uint32_t first = (i | ks) ? 1u : 0u;
+              if (TS) {
+                // D3[pt][ch] = X3[pt][k] (TMEM) . W3[ch][k] (smem): K-step ks of K-block (i & 1) = 8 packed columns
+                const uint32_t xcol = (uint32_t)(i & 1) * 32u + (uint32_t)ks * 8u;
+                if (PASSES == 2 || i < 2) {
+                  umma_ts(d, tmem_base + L::X3L_COL + xcol, wd, id, first);   // x_lo * w(_hi)
+                  umma_ts(d, tmem_base + L::X3H_COL + xcol, wd, id, 1u);      // x_hi * w(_hi)
+                } else {
+                  umma_ts(d, tmem_base + L::X3H_COL + xcol, wd, id, 1u);      // x_hi * w_lo
+                }
+              } else if (PASSES == 2 || i < 2) {
+                umma(d, wd, umma_desc(x3_s + 2 * PIECE + kb + koff), id, first);   // w(_hi) * x_lo
+                umma(d, wd, umma_desc(x3_s + kb + koff), id, 1u);                  // w(_hi) * x_hi
               } else {
-                umma(d, ad, umma_desc(x3_s + kb + koff), id, 1u);                               // w_lo * x_hi
+                umma(d, wd, umma_desc(x3_s + kb + koff), id, 1u);                  // w_lo * x_hi
               }
             }
             umma_commit(smem_u32(&S.free_bar[slot]));
@@ -433,9 +498,44 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_full; dd[3] = t_accf; dd[4] = t_x12; dd[5] = my_tiles;
     }
   } else if (warp >= NFRONT) {
-    // ======================= max warps: L3 epilogue, thread = output channel =======================
+    // ======================= max warps: L3 epilogue =======================
     const int q = warp & 3;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    if (TS) {
+      // D3[pt][ch]: lanes = points.  Each warp folds its 32 points per channel with the exchange network, the four
+      // warps meet in the shared running max.
+      for (int it = 0; it < my_tiles; it++) {
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; c++) {
+          const int buf = c & 1;
+          const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);
+          mbar_wait(smem_u32(&S.acc_bar[buf]), use & 1u);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_sel + (uint32_t)buf * 128u;
+          float r4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (!(a.exp_flags & 2)) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float v[32];
+            tmem_ld32(taddr + (uint32_t)j * 32u, v);
+            r4[j] = warp_colmax32(v, lane);
+          }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&S.accfree_bar[buf]));
+#pragma unroll
+          for (int j = 0; j < 4; j++) atomicMax(&S.gmax_s[c * 128 + j * 32 + lane], cg_f2key(r4[j]));
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");   // all four max warps have folded their last chunk
+      for (int ch = tid - NFT; ch < 1024; ch += NMAXW * 32) {
+        float m = cg_key2f(S.gmax_s[ch]) + __ldg(&a.l3.b[ch]);   // bias is constant over points: add after the max
+        if (a.relu3) m = fmaxf(m, 0.f);
+        atomicMax(&a.gmax_keys[(size_t)b * 1024 + ch], cg_f2key(m));
+      }
+    } else {
+    // D3[ch][pt]: thread = output channel, the max over the tile's points is a per-thread reduction over columns
     float run[NCHUNK];
 #pragma unroll
     for (int c = 0; c < NCHUNK; c++) run[c] = -INFINITY;
@@ -449,7 +549,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
         const uint32_t taddr = tmem_base + lane_sel + (uint32_t)buf * 128u;
         float m = run[c];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < ((a.exp_flags & 2) ? 0 : 4); j++) {
           float v[32];
           tmem_ld32(taddr + (uint32_t)j * 32u, v);
 #pragma unroll
@@ -467,6 +567,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       float m = run[c] + __ldg(&a.l3.b[ch]);   // bias is constant over points: add after the max
       if (a.relu3) m = fmaxf(m, 0.f);
       atomicMax(&a.gmax_keys[(size_t)b * 1024 + ch], cg_f2key(m));
+    }
     }
   } else {
     // ======================= front warps: thread = (point, channel half) =======================
@@ -493,6 +594,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     };
     // 6 -> 64 (+bias, ReLU) of the prefetched row -> this thread's 32-channel slice of the XA tile
     auto layer0 = [&]() {
+      if (a.exp_flags & 4) { fence_proxy_async(); bar_front(); return; }
       float v[6];
       if (a.in.x_direct) {
 #pragma unroll
@@ -542,6 +644,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     auto l1_epilogue = [&](int tile, int it) {
       mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
       tc_fence_after();
+      if (a.exp_flags & 4) { tc_fence_before(); bar_front(); if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar)); return; }
       float v[32];
       tmem_ld32(tmem_base + lane_sel + D1_COL + (uint32_t)half * 32u, v);
       if (a.stage1_mode == 1) {
@@ -584,7 +687,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       //    L3 has let go of X3, so only 16 x st.shared.v4 sit between two tiles' L3 streams
       uint32_t ph[2][4][4], pl[2][4][4];
 #pragma unroll
-      for (int j32 = 0; j32 < 2; j32++) {
+      for (int j32 = 0; j32 < ((a.exp_flags & 4) ? 0 : 2); j32++) {
         float v[32];
         tmem_ld32(tmem_base + lane_sel + D2_COL + (uint32_t)half * 64u + (uint32_t)j32 * 32u, v);
 #pragma unroll
@@ -593,17 +696,26 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
         for (int cc = 0; cc < 4; cc++) pack_hilo8<PASSES == 2>(v + cc * 8, ph[j32][cc], pl[j32][cc]);
       }
       if (it >= 1) mbar_wait(smem_u32(&S.tile_bar), (uint32_t)(it - 1) & 1u);
+      if (a.exp_flags & 4) {
+      } else if (TS) {
+        // word j of this thread = channels (half*64 + 2j, +1) of its point = packed K column half*32 + j
+        tc_fence_after();
+        tmem_st32(tmem_base + lane_sel + L::X3H_COL + (uint32_t)half * 32u, &ph[0][0][0]);
+        tmem_st32(tmem_base + lane_sel + L::X3L_COL + (uint32_t)half * 32u, &pl[0][0][0]);
+        tmem_st_wait();
+      } else {
 #pragma unroll
-      for (int j32 = 0; j32 < 2; j32++)
+        for (int j32 = 0; j32 < 2; j32++)
 #pragma unroll
-        for (int cc = 0; cc < 4; cc++) {
-          // channel = half*64 + j32*32 + cc*8 ..  ->  K-block `half`, 16-byte chunk j32*4 + cc
-          const uint32_t off = (uint32_t)half * PIECE + row_chunk_off(p, j32 * 4 + cc);
-          *reinterpret_cast<uint4 *>(x3 + off) = make_uint4(ph[j32][cc][0], ph[j32][cc][1], ph[j32][cc][2], ph[j32][cc][3]);
-          *reinterpret_cast<uint4 *>(x3 + 2 * PIECE + off) = make_uint4(pl[j32][cc][0], pl[j32][cc][1], pl[j32][cc][2], pl[j32][cc][3]);
-        }
+          for (int cc = 0; cc < 4; cc++) {
+            // channel = half*64 + j32*32 + cc*8 ..  ->  K-block `half`, 16-byte chunk j32*4 + cc
+            const uint32_t off = (uint32_t)half * PIECE + row_chunk_off(p, j32 * 4 + cc);
+            *reinterpret_cast<uint4 *>(x3 + off) = make_uint4(ph[j32][cc][0], ph[j32][cc][1], ph[j32][cc][2], ph[j32][cc][3]);
+            *reinterpret_cast<uint4 *>(x3 + 2 * PIECE + off) = make_uint4(pl[j32][cc][0], pl[j32][cc][1], pl[j32][cc][2], pl[j32][cc][3]);
+          }
+        fence_proxy_async();
+      }
       tc_fence_before();
-      fence_proxy_async();
       bar_front();
       if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
       // B. 6 -> 64 of the NEXT tile (inputs were prefetched a tile ago)
@@ -688,8 +800,10 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_REQUIRE(ctx, a.tc_img != nullptr, "trunk: tensor-core weight image missing");
   static bool attr_set = false;
   if (!attr_set) {
-    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_set = true;
   }
   const int ntiles = (a.N + TP - 1) / TP;
@@ -698,6 +812,19 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   const int tiles_per_cta = (ntiles + splits - 1) / splits;
   dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, a.B);
   const bool two_pass = ctx->engine == 2 && a.tc_f16_ok;
+  static const bool ts_mode = getenv("CG_TRUNK_SS") == nullptr;   // A operand of L3 from TMEM unless CG_TRUNK_SS is set
+  static const int exp_flags = getenv("CG_TRUNK_EXP") ? atoi(getenv("CG_TRUNK_EXP")) : 0;
+  auto launch = [&](const cg_trunk_args &a0) {
+    cg_trunk_args aa = a0;
+    aa.exp_flags = exp_flags;
+    if (two_pass) {
+      if (ts_mode) trunk_tc_kernel<2, true><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(aa, tiles_per_cta);
+      else trunk_tc_kernel<2, false><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(aa, tiles_per_cta);
+    } else {
+      if (ts_mode) trunk_tc_kernel<3, true><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(aa, tiles_per_cta);
+      else trunk_tc_kernel<3, false><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(aa, tiles_per_cta);
+    }
+  };
   static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
   if (debug) {
     cg_trunk_args ad = a;
@@ -706,8 +833,7 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
     CG_CUDA(ctx, cudaMalloc(&d_dbg, n * 64));
     CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, n * 64, ctx->stream));
     ad.dbg = d_dbg;
-    if (two_pass) trunk_tc_kernel<2><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(ad, tiles_per_cta);
-    else trunk_tc_kernel<3><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(ad, tiles_per_cta);
+    launch(ad);
     CG_LAUNCH_CHECK(ctx);
     std::vector<unsigned long long> h(n * 8);
     CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -721,8 +847,7 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
             n, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles, s[3] / tiles);
     return CG_OK;
   }
-  if (two_pass) trunk_tc_kernel<2><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
-  else trunk_tc_kernel<3><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(a, tiles_per_cta);
+  launch(a);
   CG_LAUNCH_CHECK(ctx);
   return CG_OK;
 }
