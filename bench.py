@@ -387,8 +387,12 @@ def main():
     flops_per_launch = trunk_flops_per_step * args.steps / max(trunk_n, 1)
     achieved = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "trunk_traffic.json")
+    if os.path.exists(tpath):   # dram bytes per launch of the trunk from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get("mean_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "trunk (fused shared-MLP 6-64-[64]-128-1024 + max)",
+                "traffic": traffic, "kernel": "trunk (fused shared-MLP 6-64-[64]-128-1024 + max)",
                 "engine": ["fp32-simt", "tcgen05-bf16x3", "tcgen05-f16x2"][main_engine],
                 "launches_timed": int(trunk_n), "avg_launch_ms": per_launch_ms,
                 "share_of_step": trunk_ms / ms, "peak_source": f"{peaks['source']} bf16 dense, sustained",
