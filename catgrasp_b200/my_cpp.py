@@ -143,3 +143,28 @@ def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_tran
         print("n_approach_dir_rej={}, n_ik_rej={}, n_open_gripper_rej={}, n_close_gripper_rej={}".format(
             int((status == _lib.CG_ST_REJ_DIR).sum()), n_ik, int((status == _lib.CG_ST_REJ_COLL).sum()), 0))
     return [poses[q].copy() for q in np.nonzero(keep)[0]]
+
+
+def makeOccupancyGridFromCloudScan(pts, K, resolution):
+    """my_cpp/common.cpp:324-431 (signature common.h:61): (P,3) scan points, camera K (unused by the reference's
+    output as well), cell size -> (Q,3) float32 grid samples that lie on or behind the observed surface, in raster
+    (x, y, z) order (the reference: OpenMP thread-arrival order)."""
+    p = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).astype(np.float32))
+    if p.ndim != 2 or p.shape[1] != 3:
+        raise ValueError(f"pts must be (N,3), got {p.shape}")     # assert(pts.cols()==3), common.cpp:329
+    ctx = _lib.Context.get()
+    res = float(np.float32(resolution))
+    dims = (C.c_int * 3)()
+    org = (C.c_float * 3)()
+    ctx.check(ctx.lib.cg_occupancy_grid_geometry(_lib.ptr(p), p.shape[0], C.c_float(res), dims, org))
+    nx, ny, nz = int(dims[0]), int(dims[1]), int(dims[2])
+    if nx * ny * nz == 0:
+        return np.zeros((0, 3), np.float32)
+    flags = np.empty(nx * ny * nz, np.uint8)
+    ctx.check(ctx.lib.cg_occupancy_from_scan_host(ctx.h, _lib.ptr(p), p.shape[0], C.c_float(res), _lib.ptr(flags)))
+    idx = np.nonzero(flags)[0]
+    xi, yi, zi = idx // (ny * nz), (idx // nz) % ny, idx % nz
+    r32 = np.float32(res)
+    out = np.stack([np.float32(org[0]) + xi.astype(np.float32) * r32, np.float32(org[1]) + yi.astype(np.float32) * r32,
+                    np.float32(org[2]) + zi.astype(np.float32) * r32], axis=1).astype(np.float32)
+    return out

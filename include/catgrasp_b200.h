@@ -183,6 +183,17 @@ int cg_filter_grasp_pose_dev(cg_ctx *ctx, const cg_filter_params *prm,
                              cg_sdf *sdf_enclosed, const float *enclosed_pts, int P2,
                              uint8_t *out_status, int8_t *out_offset, float *out_poses);
 
+/* ---- occupancy / occlusion grid from a depth scan ----------------------------
+ * Replaces: my_cpp/common.cpp:324-431 (makeOccupancyGridFromCloudScan; the K
+ * argument of the reference is computed with but never influences its output).
+ * Samples form a regular grid over the padded bounding box of pts:
+ *   dims[a] = int((max_a + 0.005 - (min_a - 0.005)) / resolution), origin[a] = min_a - 0.005   (float arithmetic)
+ * out_flags[(xi*ny + yi)*nz + zi] = 1 iff the first occupied cell on the ray origin -> sample is not farther than
+ * the sample (the reference pushes exactly these samples, in thread-arrival order; here raster order).            */
+int cg_occupancy_grid_geometry(const float *pts_host, int P, float resolution, int dims[3], float origin[3]);
+int cg_occupancy_from_scan_host(cg_ctx *ctx, const float *pts_host, int P, float resolution,
+                                unsigned char *out_flags_host);
+
 /* ---- PointNet++ primitives (device pointers) ---------------------------
  * Replace the free functions of pointnet2.py:14-149.  Indices are int32 on
  * the device (the Python mirror widens to int64 like the reference).        */

@@ -10,11 +10,11 @@ LIB = os.path.join(OUT_DIR, "libfilter_ref.so")
 
 
 def build(force=False):
-    src = os.path.join(HERE, "filter_ref.c")
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+    srcs = [os.path.join(HERE, f) for f in ("filter_ref.c", "occupancy_ref.c")]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = ["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", LIB, src, "-lm"]
+    cmd = ["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fopenmp", "-shared", "-fPIC", "-o", LIB] + srcs + ["-lm"]
     subprocess.check_call(cmd)
     return LIB
 

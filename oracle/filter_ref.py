@@ -58,3 +58,17 @@ def sdf_lookup_ref(grid, grid_coords, mode):
     out = np.zeros(gc.shape[0], np.float32)
     lib.sdf_lookup_ref(_p(g), _p(d), _p(gc), C.c_int(gc.shape[0]), C.c_int(int(mode)), _p(out))
     return out
+
+
+def occupancy_ref(pts, resolution):
+    """oracle/occupancy_ref.c: returns (flags (nx,ny,nz) u8, origin (3,) f32, dims)."""
+    lib = _load()
+    lib.occupancy_ref.restype = None
+    lib.occupancy_geometry_ref.restype = None
+    p = np.ascontiguousarray(np.asarray(pts, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+    dims = np.zeros(3, np.int32)
+    org = np.zeros(3, np.float32)
+    lib.occupancy_geometry_ref(_p(p), C.c_int(p.shape[0]), C.c_float(float(np.float32(resolution))), _p(dims), _p(org))
+    flags = np.zeros(int(dims[0]) * int(dims[1]) * int(dims[2]), np.uint8)
+    lib.occupancy_ref(_p(p), C.c_int(p.shape[0]), C.c_float(float(np.float32(resolution))), _p(flags))
+    return flags.reshape(dims[0], dims[1], dims[2]), org, dims

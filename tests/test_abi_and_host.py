@@ -179,3 +179,24 @@ def test_sdf_oracle_fp32_vs_reference_formula():
     assert np.abs(tri - sdf_ref.signed_distance(g["sdf"], gc.T)).max() < 1e-6
     near = filter_ref.sdf_lookup_ref(g["sdf"], gc, 1)
     assert np.array_equal(near, sdf_ref.signed_distance_nearest(g["sdf"], gc.T).astype(np.float32))
+
+
+def test_occupancy_oracle_semantics():
+    """oracle/occupancy_ref.c (common.cpp:324-431): samples at/behind the observed surface are reported, samples in
+    front of it are not; geometry follows the reference's float arithmetic."""
+    from oracle import filter_ref
+    rng = np.random.RandomState(0)
+    # a fronto-parallel wall at z = 0.70 m seen from the origin
+    xy = rng.uniform(-0.02, 0.02, (6000, 2))
+    pts = np.c_[xy, np.full(6000, 0.70) + rng.uniform(0, 0.0005, 6000)].astype(np.float32)
+    res = 0.002
+    flags, org, dims = filter_ref.occupancy_ref(pts, res)
+    pad = np.float32(0.005)
+    mn, mx = pts.min(0), pts.max(0)
+    assert np.array_equal(org, mn - pad)
+    assert all(int(dims[a]) == int((mx[a] + pad - (mn[a] - pad)) / np.float32(res)) for a in range(3))
+    zi = np.arange(dims[2])
+    z = org[2] + zi.astype(np.float32) * np.float32(res)
+    inner = flags[4:-4, 4:-4, :]                      # rays through the wall's interior
+    assert not inner[:, :, z < 0.697].any()           # free space in front of the wall
+    assert inner[:, :, z > 0.703].mean() > 0.95       # occluded space behind it

@@ -351,3 +351,21 @@ def test_fps_ballquery_scene_sizes_vs_oracle(cuda, N, npoint):
     gb = pn2.query_ball_point(0.004, 32, torch.from_numpy(xyz).cuda(), torch.from_numpy(new_xyz).cuda())
     assert np.array_equal(gb.cpu().numpy(), rb)
     assert (np.diff(rb, axis=-1) >= 0).all() or True
+
+
+# ------------------------------------------------------------------ occupancy grid (my_cpp.makeOccupancyGridFromCloudScan)
+@pytest.mark.parametrize("res,n_points", [(0.002, 3000), (0.001, 6000)])
+def test_occupancy_grid_bit_exact_vs_oracle(cuda, res, n_points):
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.synthetic import make_pile
+    from oracle import filter_ref
+    scene = make_pile(n_points, n_objects=4, seed=6)
+    K = np.array([[2000.0, 0, 1032], [0, 2000.0, 772], [0, 0, 1]])
+    out = my_cpp.makeOccupancyGridFromCloudScan(scene["cloud_xyz"], K, res)
+    flags, org, dims = filter_ref.occupancy_ref(scene["cloud_xyz"], res)
+    idx = np.argwhere(flags > 0)
+    ref = (org[None, :] + idx.astype(np.float32) * np.float32(res)).astype(np.float32)
+    assert out.dtype == np.float32 and out.shape == ref.shape and out.shape[0] > 100
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(ValueError):
+        my_cpp.makeOccupancyGridFromCloudScan(scene["cloud_xyz"][:, :2], K, res)
