@@ -1,82 +1,44 @@
-"""Host stage: 9-DoF RANSAC between the predicted NUNOCS cloud and the observed cloud.
+"""9-DoF RANSAC between the predicted NUNOCS cloud and the observed cloud (aligning.py:83-119), with all
+hypotheses scored on the GPU (csrc/cg_ransac.cu).
 
-Restates aligning.py:23-119 (``estimateAffine3D``, ``estimate9DTransform_worker``,
-``estimate9DTransform``) for the non-kdtree evaluation the predicter uses
-(predicter.py:161-164, ``use_kdtree_for_eval=False``).  It consumes the global numpy RNG
-exactly like the reference (one ``np.random.choice(len(source), 4, replace=False)`` per
-iteration, all drawn up front, aligning.py:91-97).  This stage is SURVEY.md 8(f) F1 ("next"):
-it runs on the CPU here; the inlier counting is vectorised over hypotheses in chunks.
+The host keeps exactly the reference's RNG consumption -- one ``np.random.choice(len(source), 4, replace=False)`` per
+iteration, all drawn up front (aligning.py:91-97) -- and the reference's selection rule (first maximum of the inlier
+ratio over the hypotheses that survive the gates, aligning.py:105-117).
 """
+import ctypes as C
+
 import numpy as np
 
-
-def _to_homo(pts):
-    return np.concatenate((pts, np.ones((pts.shape[0], 1))), axis=-1)
-
-
-def estimateAffine3D(source, target, PassThreshold):
-    """aligning.py:23-33."""
-    import cv2
-    ret, transform, inliers = cv2.estimateAffine3D(source, target, confidence=0.999, ransacThreshold=PassThreshold)
-    tmp = np.eye(4)
-    tmp[:3] = transform
-    inliers = np.where(inliers > 0)[0]
-    return tmp, inliers
-
-
-def _hypothesis(cur_src, cur_dst, target, PassThreshold, max_scale, min_scale, max_dimensions):
-    """aligning.py:36-63: one 4-point affine -> scale gates -> orthogonalised R*diag(scales), or None."""
-    transform, _ = estimateAffine3D(source=cur_src, target=cur_dst, PassThreshold=PassThreshold)
-    new_transform = transform.copy()
-    scales = np.linalg.norm(transform[:3, :3], axis=0)
-    if (scales > max_scale).any() or (scales < min_scale).any():
-        return None
-    R = transform[:3, :3] / scales.reshape(1, 3)
-    u, s, vh = np.linalg.svd(R)
-    if s.min() < 0.8 or s.max() > 1.2:
-        return None
-    R = u @ vh
-    if np.linalg.det(R) < 0:
-        return None
-    new_transform[:3, :3] = R @ np.diag(scales)
-    transform = new_transform.copy()
-    if max_dimensions is not None:
-        cloud_at_canonical = (np.linalg.inv(transform) @ _to_homo(target).T).T[:, :3]
-        dimensions = cloud_at_canonical.max(axis=0) - cloud_at_canonical.min(axis=0)
-        if (dimensions > max_dimensions).any():
-            return None
-    return transform
+from . import _lib
 
 
 def estimate9DTransform(source, target, PassThreshold, max_iter=1000, use_kdtree_for_eval=False,
                         kdtree_eval_resolution=None, max_scale=np.array([99, 99, 99]),
                         min_scale=np.array([0, 0, 0]), max_dimensions=None):
-    """aligning.py:83-119.  Returns (best_transform (4,4), inliers) or (None, None)."""
+    """Returns (best_transform (4,4) float64, inliers) or (None, None), like aligning.py:83-119."""
     if use_kdtree_for_eval:
-        raise NotImplementedError("kd-tree evaluation (aligning.py:68-79) needs open3d; the predicter never enables it")
-    source = np.asarray(source, dtype=np.float64)
-    target = np.asarray(target, dtype=np.float64)
-    max_scale = np.asarray(max_scale, dtype=np.float64)
-    min_scale = np.asarray(min_scale, dtype=np.float64)
-    srcs, dsts = [], []
-    for _ in range(max_iter):                                   # aligning.py:91-97
-        ids = np.random.choice(len(source), size=4, replace=False)
-        srcs.append(source[ids])
-        dsts.append(target[ids])
-    transforms = []
-    for i in range(len(srcs)):                                  # aligning.py:99-104
-        T = _hypothesis(srcs[i], dsts[i], target, PassThreshold, max_scale, min_scale, max_dimensions)
-        if T is not None:
-            transforms.append(T)
-    if len(transforms) == 0:
+        raise NotImplementedError("kd-tree evaluation (aligning.py:68-79) is never enabled by the predicter")
+    source = np.ascontiguousarray(source, dtype=np.float64)
+    target = np.ascontiguousarray(target, dtype=np.float64)
+    N = source.shape[0]
+    ids = np.empty((max_iter, 4), dtype=np.int32)
+    for i in range(max_iter):                                   # aligning.py:91-97
+        ids[i] = np.random.choice(len(source), size=4, replace=False)
+    ctx = _lib.Context.get()
+    mins = np.ascontiguousarray(np.asarray(min_scale, dtype=np.float64).reshape(3))
+    maxs = np.ascontiguousarray(np.asarray(max_scale, dtype=np.float64).reshape(3))
+    mdim = None if max_dimensions is None else np.ascontiguousarray(np.asarray(max_dimensions, dtype=np.float64).reshape(3))
+    ratio = np.empty(max_iter, np.float64)
+    T = np.empty((max_iter, 4, 4), np.float64)
+    valid = np.empty(max_iter, np.uint8)
+    ctx.check(ctx.lib.cg_ransac9d_host(ctx.h, _lib.ptr(source), _lib.ptr(target), N, _lib.ptr(ids), max_iter,
+                                       C.c_double(float(PassThreshold)), _lib.ptr(mins), _lib.ptr(maxs), _lib.ptr(mdim),
+                                       _lib.ptr(ratio), _lib.ptr(T), _lib.ptr(valid)))
+    keep = np.nonzero(valid)[0]
+    if keep.size == 0:
         return None, None
-    src_h = _to_homo(source)
-    ratios = np.empty(len(transforms))
-    for i, T in enumerate(transforms):                          # aligning.py:65-67
-        errs = np.linalg.norm((T @ src_h.T).T[:, :3] - target, axis=-1)
-        ratios[i] = np.sum(errs <= PassThreshold) / len(errs)
-    best_id = ratios.argmax()                                   # aligning.py:115
-    best_transform = transforms[best_id]
-    errs = np.linalg.norm((best_transform @ src_h.T).T[:, :3] - target, axis=-1)
+    best = keep[np.argmax(ratio[keep])]                         # first maximum among the survivors (aligning.py:115)
+    best_transform = T[best].copy()
+    errs = np.linalg.norm((best_transform @ np.c_[source, np.ones(N)].T).T[:, :3] - target, axis=-1)
     inliers = np.where(errs <= PassThreshold)[0]
     return best_transform, inliers

@@ -194,6 +194,15 @@ int cg_occupancy_grid_geometry(const float *pts_host, int P, float resolution, i
 int cg_occupancy_from_scan_host(cg_ctx *ctx, const float *pts_host, int P, float resolution,
                                 unsigned char *out_flags_host);
 
+/* ---- NUNOCS 9-DoF RANSAC hypothesis scoring -------------------------------------
+ * Replaces: aligning.py:36-81 (estimate9DTransform_worker) for H hypotheses at once.
+ *   source, target (N,3) float64 correspondences; ids (H,4) int32 = the 4-subsets (host numpy RNG, aligning.py:91-97)
+ *   out_valid[h] = hypothesis passed the scale / singular-value / det / max_dimensions gates
+ *   out_ratio[h] = inlier ratio at pass_threshold, out_T[h] = (4,4) float64 transform R diag(scales) | t           */
+int cg_ransac9d_host(cg_ctx *ctx, const double *source, const double *target, int N, const int32_t *ids, int H,
+                     double pass_threshold, const double min_scale[3], const double max_scale[3],
+                     const double *max_dims, double *out_ratio, double *out_T, unsigned char *out_valid);
+
 /* ---- PointNet++ primitives (device pointers) ---------------------------
  * Replace the free functions of pointnet2.py:14-149.  Indices are int32 on
  * the device (the Python mirror widens to int64 like the reference).        */
