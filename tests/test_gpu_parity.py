@@ -425,3 +425,94 @@ def test_nunocs_predict_full_surface(cuda, tmp_path):
     else:
         assert nocs_cloud.shape == (512, 3) and transform.shape == (4, 4)
         assert hasattr(npred, "best_ratio") and np.array_equal(npred.nocs_pose, transform)
+
+
+# ------------------------------------------------------------------ BASELINE.json configs as parity cases
+@pytest.mark.parametrize("N", [1024, 2048])
+def test_k1_single_object_crop_vs_oracle(cls_net, N):
+    """configs[0] (K1): 1024-pt crop, 64 candidates; N=2048 is the shipped config_grasp.yml n_pts (replace=True draw)."""
+    from catgrasp_b200.predicter import draw_subsample_ids
+    from catgrasp_b200.synthetic import make_candidates, make_pile
+    from oracle.transforms_ref import predict_batch
+    net, sd = cls_net
+    net.ctx.set_engine(2)
+    scene = make_pile(1024, n_objects=1, seed=3)
+    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], 64, seed=4)
+    data = {"cloud_xyz": scene["cloud_xyz"], "cloud_normal": scene["cloud_normal"]}
+    np.random.seed(0)
+    ref = predict_batch(sd, {"n_pts": N}, data, poses)
+    np.random.seed(0)
+    ids = draw_subsample_ids(1024, N, count=64)
+    probs, _ = net.graspq_host(scene["cloud_xyz"], scene["cloud_normal"], poses, ids)
+    assert max(np.abs(probs[b] - ref[b][2]).max() for b in range(64)) < PROB_TOL
+
+
+def test_k3_k5_collision_scale_subset_exact(cuda):
+    """configs[2] / configs[4] shapes for the collision half: 16 384 candidates against a 40 000-pt scene, and
+    1 048 576 candidates (collision only, `adjust_collision_pose=False` like generate_grasp.py:97).  Poses are
+    independent, so a random subset re-evaluated by the CPU oracle must agree bit for bit."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile
+    from oracle import filter_ref
+    g = make_gripper_proxy()
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    eye = np.eye(4)
+    rng = np.random.RandomState(0)
+    # K3
+    scene = make_pile(40000, n_objects=8, seed=1)
+    obj = scene["object_id"] == 3
+    p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
+    poses = make_candidates(p1, scene["cloud_normal"][obj], 16384, seed=2)
+    st, off, out = my_cpp.filter_grasp_pose_raw(poses, [eye], eye, eye, g["gripper_in_grasp"], True, True, so, p1, se, p2)
+    sel = rng.choice(16384, 384, replace=False)
+    rst, roff, rout = filter_ref.filter_ref(poses[sel], [eye], eye, eye, g["gripper_in_grasp"], True, True, 0, g["open"],
+                                            p1, g["enclosed"], p2)
+    assert np.array_equal(st[sel], rst) and np.array_equal(off[sel], roff)
+    assert np.array_equal(out[sel].view(np.uint32), rout.view(np.uint32))
+    assert 0 < (st == 0).sum() < 16384
+    # K5: 1M candidates = 4096 distinct poses x 256 jittered copies, object points only
+    base = make_candidates(p1, scene["cloud_normal"][obj], 4096, seed=5)
+    big = np.repeat(base, 256, axis=0)
+    big[:, :3, 3] += rng.normal(0, 0.0005, (big.shape[0], 3))
+    st, off, out = my_cpp.filter_grasp_pose_raw(big, [eye], eye, eye, g["gripper_in_grasp"], True, False, so, p1, None,
+                                                np.zeros((0, 3)))
+    assert st.shape == (1048576,)
+    sel = rng.choice(big.shape[0], 512, replace=False)
+    rst, roff, rout = filter_ref.filter_ref(big[sel], [eye], eye, eye, g["gripper_in_grasp"], True, False, 0, g["open"], p1,
+                                            None, np.zeros((0, 3)))
+    assert np.array_equal(st[sel], rst) and np.array_equal(off[sel], roff)
+    assert np.array_equal(out[sel].view(np.uint32), rout.view(np.uint32))
+    assert set(np.unique(off).tolist()) <= {-1, 0}          # no lateral search when adjust_collision_pose is off
+
+
+def test_k3_k4_graspq_scale_properties(cls_net):
+    """configs[2] / configs[3] shapes for the network half: 16 384 candidates on a 40 000-pt scene and a mixed batch of
+    8 scenes; size-independent properties + agreement of the two tensor-core engines."""
+    from catgrasp_b200.synthetic import make_candidates, make_pile
+    net, _ = cls_net
+    M, B, N = 40000, 16384, 1024
+    scene = make_pile(M, n_objects=8, seed=1)
+    poses = make_candidates(scene["cloud_xyz"], scene["cloud_normal"], B, seed=2)
+    rng = np.random.RandomState(0)
+    ids = np.stack([rng.permutation(M)[:N] for _ in range(128)]).astype(np.int32)
+    ids = np.ascontiguousarray(np.tile(ids, (B // 128, 1)))
+    out = {}
+    for e in (1, 2):
+        net.ctx.set_engine(e)
+        out[e], _ = net.graspq_host(scene["cloud_xyz"], scene["cloud_normal"], poses, ids)
+        assert np.isfinite(out[e]).all() and np.abs(out[e].sum(1) - 1).max() < 1e-5
+    assert np.abs(out[1] - out[2]).max() < PROB_TOL / 4
+    # K4: 8 independent scenes through the same handle give the same answers as one by one (no cross-call state)
+    net.ctx.set_engine(2)
+    scenes = [make_pile(20000, seed=10 + s) for s in range(8)]
+    first = []
+    for s, sc in enumerate(scenes):
+        ps = make_candidates(sc["cloud_xyz"], sc["cloud_normal"], 256, seed=20 + s)
+        first.append(net.graspq_host(sc["cloud_xyz"], sc["cloud_normal"], ps, ids[:256] % 20000)[0].copy())
+    for s in (7, 0, 3):
+        sc = scenes[s]
+        ps = make_candidates(sc["cloud_xyz"], sc["cloud_normal"], 256, seed=20 + s)
+        again = net.graspq_host(sc["cloud_xyz"], sc["cloud_normal"], ps, ids[:256] % 20000)[0]
+        assert np.array_equal(again.view(np.uint32), first[s].view(np.uint32))
