@@ -302,6 +302,10 @@ __global__ void nunocs_post_kernel(const float *__restrict__ logits, int P, int 
 int cg_linear_launch(cg_ctx *ctx, const float *X, int M, int K, const float *Wt, const float *bias, int N,
                      int relu, int bias_row_div, int x_is_keys, float *Y) {
   CG_REQUIRE(ctx, M > 0 && K > 0 && N > 0, "linear: bad shape");
+  {
+    const int rc = cg_linear_tc_try(ctx, X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
+    if (rc != 0) return rc < 0 ? rc : CG_OK;
+  }
   if (M <= RM) {
     linear_rows_kernel<<<(N + 63) / 64, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
     CG_LAUNCH_CHECK(ctx);

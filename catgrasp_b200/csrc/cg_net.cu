@@ -80,6 +80,13 @@ extern "C" int cg_net_create(cg_ctx *ctx, int kind, int n_out, const float *blob
                            l1[i] >= 0 ? blob_host + woff[l1[i]] : nullptr, net->tc_img[i], &net->tc_f16_ok[i]);
     if (rc != CG_OK) return rc;
   }
+  // tensor-core images of the FC / head layers
+  const int fc_layers[] = {L_S3_F1, L_S3_F2, L_SK_F1, L_SK_F2, L_SK_F3, L_HEAD0, L_HEAD1, L_HEAD2, L_HEAD3, L_HEAD4};
+  for (int li : fc_layers) {
+    if (d[li].K == 0) continue;
+    int rc = cg_linear_tc_register(ctx, net->L[li].Wt, blob_host + woff[li], d[li].K, d[li].C);
+    if (rc != CG_OK) return rc;
+  }
   CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *out = net;
   return CG_OK;
@@ -88,6 +95,7 @@ extern "C" int cg_net_create(cg_ctx *ctx, int kind, int n_out, const float *blob
 extern "C" void cg_net_destroy(cg_net *net) {
   if (!net) return;
   cudaSetDevice(net->ctx->device);
+  for (int i = 0; i < L_COUNT; i++) cg_linear_tc_unregister(net->L[i].Wt);
   cudaFree(net->blob_dev);
   for (int i = 0; i < 3; i++) cudaFree(net->tc_img[i]);
   delete net;

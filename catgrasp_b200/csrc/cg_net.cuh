@@ -73,6 +73,11 @@ int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *
 // x_is_keys: X holds order-preserving uint keys (output of a trunk) to be decoded on load.
 int cg_linear_launch(cg_ctx *ctx, const float *X, int M, int K, const float *Wt, const float *bias,
                      int N, int relu, int bias_row_div, int x_is_keys, float *Y);
+// tensor-core FC path (cg_linear_tc.cu)
+int cg_linear_tc_register(cg_ctx *ctx, const float *Wt_dev, const float *Wt_host, int K, int N);
+void cg_linear_tc_unregister(const float *Wt_dev);
+int cg_linear_tc_try(cg_ctx *ctx, const float *X, int M, int K, const float *Wt, const float *bias, int N, int relu,
+                     int bias_row_div, int x_is_keys, float *Y);
 int cg_softmax_launch(cg_ctx *ctx, const float *logits, int B, int C, float *probs, int32_t *label);
 int cg_nunocs_post_launch(cg_ctx *ctx, const float *logits, int P, int bins, float *coords,
                           float *conf_z, int32_t *out_bins);
