@@ -213,23 +213,25 @@ __host__ __device__ __forceinline__ uint32_t row_chunk_off(int row, int c16) {
   return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((c16 ^ (row & 7)) << 4);
 }
 
-// pack 8 fp32 values into 4+4 words of bf16 (or fp16) hi / lo pairs
+// pack 8 fp32 values into 4+4 words of bf16 (or fp16) hi / lo pairs, two values per conversion instruction
 template <bool FP16>
 __device__ __forceinline__ void pack_hilo8(const float *v, uint32_t *h, uint32_t *l) {
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     if (FP16) {
       const float a0 = fminf(v[2 * j], 65504.f), a1 = fminf(v[2 * j + 1], 65504.f);   // inputs are post-ReLU (>= 0)
-      const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1);
-      const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
-      h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      const __half2 hh = __floats2half2_rn(a0, a1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+      h[j] = *reinterpret_cast<const uint32_t *>(&hh);
+      l[j] = *reinterpret_cast<const uint32_t *>(&ll);
     } else {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-      h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-      l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hh);
+      const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - h0, v[2 * j + 1] - h1);
+      h[j] = hb;
+      l[j] = *reinterpret_cast<const uint32_t *>(&ll);
     }
   }
 }
@@ -253,14 +255,7 @@ __device__ __forceinline__ void store_hilo8_f16(unsigned char *hi_dst, unsigned 
 // split 8 fp32 values into bf16 hi / lo and store them as the two 16-byte chunks of an operand row
 __device__ __forceinline__ void store_hilo8(unsigned char *hi_dst, unsigned char *lo_dst, const float *v) {
   uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-    h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
+  pack_hilo8<false>(v, h, l);
   *reinterpret_cast<uint4 *>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4 *>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
