@@ -162,16 +162,23 @@ constexpr int FT = 256;
 
 __device__ bool any_point_hits(const SdfView &s, const float *inv, int mode, const float *__restrict__ pts, int P,
                                volatile int *flag) {
+  // four independent points per thread and iteration (12 loads in flight) -- the loop is latency-bound otherwise;
+  // within one j the 256 threads read consecutive points (coalesced 12-byte rows)
   bool hit = false;
-  int it = 0;
-  for (int p = threadIdx.x; p < P; p += FT, it++) {
-    if ((it & 7) == 7 && *flag) break;  // another thread already found a collision
-    const float x = __ldg(pts + 3 * (size_t)p), y = __ldg(pts + 3 * (size_t)p + 1), z = __ldg(pts + 3 * (size_t)p + 2);
-    if (point_hits(s, inv, mode, x, y, z)) {
-      hit = true;
-      *flag = 1;
-      break;
+  for (int base = 0; base < P; base += 4 * FT) {
+    float x[4], y[4], z[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int p = base + j * FT + threadIdx.x;
+      ok[j] = p < P;
+      const size_t o = 3 * (size_t)(ok[j] ? p : 0);
+      x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) hit = hit || (ok[j] && point_hits(s, inv, mode, x[j], y[j], z[j]));
+    if (hit) { *flag = 1; break; }
+    if (*flag) break;   // another thread already found a collision
   }
   return __syncthreads_or(hit) != 0;
 }

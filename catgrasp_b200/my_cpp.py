@@ -168,3 +168,90 @@ def makeOccupancyGridFromCloudScan(pts, K, resolution):
     out = np.stack([np.float32(org[0]) + xi.astype(np.float32) * r32, np.float32(org[1]) + yi.astype(np.float32) * r32,
                     np.float32(org[2]) + zi.astype(np.float32) * r32], axis=1).astype(np.float32)
     return out
+
+
+def directionVecToRotation(direction, ref):
+    """my_cpp/common.cpp:75-108 (twin of Utils.py:262-290): rotation taking ``ref`` onto ``direction``."""
+    direction = np.asarray(direction, dtype=np.float32).reshape(3).copy()
+    ref = np.asarray(ref, dtype=np.float32).reshape(3)
+    direction /= np.linalg.norm(direction)
+    v = np.cross(direction, ref)
+    if np.linalg.norm(v) < 1e-5:
+        return np.eye(3, dtype=np.float32)
+    s = np.linalg.norm(v)
+    c = float(np.dot(direction, ref))
+    vs = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]], dtype=np.float32)
+    R = (np.eye(3, dtype=np.float32) + vs + vs @ vs * (1 - c) / (s * s)).T
+    u, _, vt = np.linalg.svd(R)
+    return (u @ vt).astype(np.float32)
+
+
+def augmentGraspPoses(R0, selected_point, sphere_pts, inplane_rot_step, hand_depth, approach_step, init_bite):
+    """my_cpp/common.cpp:111-153 (exported by pybind.cpp:20, no Python caller in the reference): the cone enumeration
+    R0 * R_sphere * R_inplane x approach depths.  The reference iterates ``sphere_pts.size()`` (rows*3, an
+    out-of-bounds read); this mirror iterates the rows."""
+    R0 = np.asarray(R0, dtype=np.float32).reshape(3, 3)
+    selected_point = np.asarray(selected_point, dtype=np.float32).reshape(3)
+    sphere_pts = np.asarray(sphere_pts, dtype=np.float32).reshape(-1, 3)
+    Rs = [R0]
+    for sp in sphere_pts:
+        R_sphere = directionVecToRotation(sp, np.array([1, 0, 0], np.float32))
+        x_rot = np.float32(0)
+        while x_rot < 180:                                   # for (float x_rot=0; x_rot<180; x_rot+=inplane_rot_step)
+            a = float(x_rot) / 180.0 * np.pi
+            ca, sa = np.cos(a), np.sin(a)
+            R_inplane = np.array([[1, 0, 0], [0, ca, -sa], [0, sa, ca]], dtype=np.float32)
+            Rs.append(R0 @ R_sphere @ R_inplane)
+            x_rot = np.float32(x_rot + np.float32(inplane_rot_step))
+    out = []
+    for R in Rs:
+        u, _, vt = np.linalg.svd(R)
+        R = (u @ vt).astype(np.float32)
+        approach_dir = R[:, 0]
+        d = np.float32(0)
+        while d < hand_depth:                                # for (float d=0; d<hand_depth; d+=approach_step)
+            T = np.eye(4, dtype=np.float32)
+            T[:3, :3] = R
+            T[:3, 3] = selected_point + np.float32(init_bite) * approach_dir + approach_dir * d
+            out.append(T)
+            d = np.float32(d + np.float32(approach_step))
+    return out
+
+
+class CollisionManager:
+    """my_cpp/collision_manager.h:33-52 (exported by pybind.cpp:13-18, no Python caller): one posed mesh against one
+    point set.  The mesh is represented by its registered SDF (see register_gripper_sdf); isAnyCollision() evaluates
+    the same predicate as filterGraspPose for the single transform set with setTransform()."""
+
+    def __init__(self):
+        self._sdf = None
+        self._pts = np.zeros((0, 3), np.float32)
+        self._pose = np.eye(4, dtype=np.float32)
+
+    def registerMesh(self, vertices, faces):
+        vertices, faces = np.asarray(vertices), np.asarray(faces)
+        if vertices.ndim != 2 or vertices.shape[1] != 3 or faces.ndim != 2 or faces.shape[1] != 3:
+            raise ValueError("registerMesh: V,F must be (N,3)")                  # collision_manager.cpp:17-27 (exit(1))
+        self._sdf = _sdf_for(vertices, faces)
+        return 0
+
+    def registerPointCloud(self, pts, resolution):
+        pts = np.asarray(pts)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise ValueError("registerPointCloud: pts must be (N,3)")            # collision_manager.cpp:57-61
+        self._pts = np.ascontiguousarray(pts, dtype=np.float32)
+        return 1
+
+    def setTransform(self, pose, ob_id):
+        pose = np.asarray(pose)
+        if pose.shape != (4, 4):
+            raise ValueError("setTransform: pose must be (4,4)")                 # collision_manager.cpp:83-87
+        self._pose = pose.astype(np.float32)
+
+    def isAnyCollision(self):
+        if self._sdf is None:
+            raise _lib.CgError("CollisionManager: registerMesh first")
+        eye = np.eye(4)
+        st, _, _ = filter_grasp_pose_raw(self._pose[None], eye[None], eye, eye, eye, False, False, self._sdf, self._pts,
+                                         None, np.zeros((0, 3), np.float32))
+        return bool(st[0] == _lib.CG_ST_REJ_COLL)

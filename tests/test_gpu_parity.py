@@ -516,3 +516,31 @@ def test_k3_k4_graspq_scale_properties(cls_net):
         ps = make_candidates(sc["cloud_xyz"], sc["cloud_normal"], 256, seed=20 + s)
         again = net.graspq_host(sc["cloud_xyz"], sc["cloud_normal"], ps, ids[:256] % 20000)[0]
         assert np.array_equal(again.view(np.uint32), first[s].view(np.uint32))
+
+
+def test_my_cpp_module_surface(cuda):
+    """Every name exported by my_cpp/pybind.cpp:11-23 exists and behaves: CollisionManager, augmentGraspPoses."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_gripper_proxy
+    g = make_gripper_proxy()
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    my_cpp.register_gripper_sdf(g["open"]["V"], g["open"]["F"], so)
+    cm = my_cpp.CollisionManager()
+    assert cm.registerMesh(g["open"]["V"], g["open"]["F"]) == 0
+    inside = np.array([[-0.02, 0.0, 0.0], [0.5, 0.5, 0.5]])                 # first point sits in the palm
+    cm.registerPointCloud(inside, 0.0005)
+    cm.setTransform(np.eye(4), 0)
+    assert cm.isAnyCollision() is True
+    far = np.eye(4); far[:3, 3] = [1.0, 1.0, 1.0]
+    cm.setTransform(far, 0)
+    assert cm.isAnyCollision() is False
+    with pytest.raises(ValueError):
+        cm.registerPointCloud(inside[:, :2], 0.0005)
+    R0 = np.eye(3)
+    sph = np.array([[1.0, 0.2, 0.0], [0.9, 0.0, 0.3]])
+    poses = my_cpp.augmentGraspPoses(R0, np.array([0.1, 0.2, 0.7]), sph, 30.0, 0.012, 0.003, 0.005)
+    assert len(poses) == (1 + 2 * 6) * 4 and all(p.shape == (4, 4) and p.dtype == np.float32 for p in poses)
+    P = np.stack(poses)
+    assert np.abs(np.einsum("nij,nkj->nik", P[:, :3, :3], P[:, :3, :3]) - np.eye(3)).max() < 1e-5
+    assert np.allclose(P[0, :3, 3], [0.105, 0.2, 0.7], atol=1e-6) and np.allclose(P[1, :3, 3] - P[0, :3, 3], [0.003, 0, 0], atol=1e-6)
