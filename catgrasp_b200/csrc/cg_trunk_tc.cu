@@ -53,7 +53,11 @@ template <bool TS> struct Lay {
   static constexpr uint32_t RING_OFF = TS ? 5 * PIECE : 9 * PIECE;
   static constexpr uint32_t MISC_OFF = 13 * PIECE;          // 208 KB in both variants
   // TMEM columns: D3 x2 at 0 / 128;  SS: D1 256, D2 320;  TS: D2 256 (D1 aliases it), X3 hi 384, X3 lo 448
-  static constexpr uint32_t D1_COL = 256, D2_COL = TS ? 256 : 320, X3H_COL = 384, X3L_COL = 448;
+  // SS: D1 256, D2 320.  TS: two 128-column activation buffers XB(it) = 256 + (it & 1) * 128; D1 and D2 of tile `it`
+  // land in XB(it) and the L2 epilogue converts D2 in place into X3 hi (64 cols) | X3 lo (64 cols), so the L3 input
+  // tile is double-buffered without extra columns and tile t+1's front layers never wait for tile t's L3 stream.
+  static constexpr uint32_t D1_COL = 256, D2_COL = TS ? 256 : 320;
+  static __host__ __device__ constexpr uint32_t xb(int it) { return TS ? 256u + (uint32_t)(it & 1) * 128u : 0u; }
 };
 constexpr int NSLOT_MAX = 8;
 constexpr int NCHUNK = 8;                  // 1024 output channels / 128
@@ -171,20 +175,17 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Column-wise max over the 32 lanes of a warp for 32 columns at once: after the five exchange rounds thread t holds
-// max over lanes of column t (31 shuffles instead of 5 x 32).
-__device__ __forceinline__ float warp_colmax32(float *v, int lane) {
+// Column-wise max over the 32 lanes of a warp for 32 columns: one warp-wide fp32 max reduction per column
+// (redux.sync.max.f32 -> CREDUX.MAX.F32 into a uniform register); thread t keeps the result of column t.
+__device__ __forceinline__ float warp_colmax32(const float *v, int lane) {
+  float mine = 0.f;
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; i++) {
-      const float keep = up ? v[i + off] : v[i];
-      const float send = up ? v[i] : v[i + off];
-      v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
-    }
+  for (int i = 0; i < 32; i++) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v[i]));
+    mine = (lane == i) ? r : mine;
   }
-  return v[0];
+  return mine;
 }
 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       mbar_wait(smem_u32(&S.x1_bar), ph_x1); ph_x1 ^= 1u;
       tc_fence_after();
       if (elect_one()) {
-        issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
+        issue_k64(tmem_base + (TS ? L::xb(0) : D1_COL), xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
         umma_commit(l1b);
       }
       __syncwarp();
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
     mbar_wait(smem_u32(&S.x2_bar), ph_x2); ph_x2 ^= 1u;
     tc_fence_after();
     if (elect_one()) {
-      issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
+      issue_k64(tmem_base + (TS ? L::xb(0) : D2_COL), xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
       umma_commit(l2b);
     }
     __syncwarp();
@@ -442,10 +443,10 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
                 // D3[pt][ch] = X3[pt][k] (TMEM) . W3[ch][k] (smem): K-step ks of K-block (i & 1) = 8 packed columns
                 const uint32_t xcol = (uint32_t)(i & 1) * 32u + (uint32_t)ks * 8u;
                 if (PASSES == 2 || i < 2) {
-                  umma_ts(d, tmem_base + L::X3L_COL + xcol, wd, id, first);   // x_lo * w(_hi)
-                  umma_ts(d, tmem_base + L::X3H_COL + xcol, wd, id, 1u);      // x_hi * w(_hi)
+                  umma_ts(d, tmem_base + L::xb(it) + 64u + xcol, wd, id, first);   // x_lo * w(_hi)
+                  umma_ts(d, tmem_base + L::xb(it) + xcol, wd, id, 1u);            // x_hi * w(_hi)
                 } else {
-                  umma_ts(d, tmem_base + L::X3H_COL + xcol, wd, id, 1u);      // x_hi * w_lo
+                  umma_ts(d, tmem_base + L::xb(it) + xcol, wd, id, 1u);            // x_hi * w_lo
                 }
               } else if (PASSES == 2 || i < 2) {
                 umma(d, wd, umma_desc(x3_s + 2 * PIECE + kb + koff), id, first);   // w(_hi) * x_lo
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           t_x12 += clock64() - tw;
           tc_fence_after();
           if (elect_one()) {
-            issue_k64(tmem_base + D1_COL, xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
+            issue_k64(tmem_base + (TS ? L::xb(it + 1) : D1_COL), xa_s, PIECE, w1_s, 8192u, idesc(128, 64));
             umma_commit(l1b);
           }
           __syncwarp();
@@ -481,7 +482,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
           t_x12 += clock64() - tw;
           tc_fence_after();
           if (elect_one()) {
-            issue_k64(tmem_base + D2_COL, xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
+            issue_k64(tmem_base + (TS ? L::xb(it + 1) : D2_COL), xa_s, PIECE, w2_s, PIECE, idesc(128, 128));
             umma_commit(l2b);
           }
           __syncwarp();
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
       tc_fence_after();
       if (a.exp_flags & 4) { tc_fence_before(); bar_front(); if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar)); return; }
       float v[32];
-      tmem_ld32(tmem_base + lane_sel + D1_COL + (uint32_t)half * 32u, v);
+      tmem_ld32(tmem_base + lane_sel + (TS ? L::xb(it) : D1_COL) + (uint32_t)half * 32u, v);
       if (a.stage1_mode == 1) {
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias1[half * 32 + j], 0.f);
@@ -684,19 +685,22 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
       for (int j32 = 0; j32 < ((a.exp_flags & 4) ? 0 : 2); j32++) {
         float v[32];
-        tmem_ld32(tmem_base + lane_sel + D2_COL + (uint32_t)half * 64u + (uint32_t)j32 * 32u, v);
+        tmem_ld32(tmem_base + lane_sel + (TS ? L::xb(it) : D2_COL) + (uint32_t)half * 64u + (uint32_t)j32 * 32u, v);
 #pragma unroll
         for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias2[half * 64 + j32 * 32 + j], 0.f);
 #pragma unroll
         for (int cc = 0; cc < 4; cc++) pack_hilo8<PASSES == 2>(v + cc * 8, ph[j32][cc], pl[j32][cc]);
       }
-      if (it >= 1) mbar_wait(smem_u32(&S.tile_bar), (uint32_t)(it - 1) & 1u);
+      if (!TS && it >= 1) mbar_wait(smem_u32(&S.tile_bar), (uint32_t)(it - 1) & 1u);
       if (a.exp_flags & 4) {
       } else if (TS) {
         // word j of this thread = channels (half*64 + 2j, +1) of its point = packed K column half*32 + j
+        // in-place conversion of XB(it): every front thread must have pulled its fp32 half-row out of D2 first
+        tc_fence_before();
+        bar_front();
         tc_fence_after();
-        tmem_st32(tmem_base + lane_sel + L::X3H_COL + (uint32_t)half * 32u, &ph[0][0][0]);
-        tmem_st32(tmem_base + lane_sel + L::X3L_COL + (uint32_t)half * 32u, &pl[0][0][0]);
+        tmem_st32(tmem_base + lane_sel + L::xb(it) + (uint32_t)half * 32u, &ph[0][0][0]);
+        tmem_st32(tmem_base + lane_sel + L::xb(it) + 64u + (uint32_t)half * 32u, &pl[0][0][0]);
         tmem_st_wait();
       } else {
 #pragma unroll
