@@ -363,17 +363,19 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 
   if (warp == PROD_WARP) {
     // ======================= producer: stream W3 pieces through the ring =======================
-    const int total = my_tiles * NCHUNK * PPC;
+    // pieces travel in pairs (32 KB, adjacent in the image and in the ring): one mbarrier round trip per pair
+    constexpr int NPAIR = NSLOT / 2, PAIR_SHIFT = L::SLOT_SHIFT - 1;
+    const int total = my_tiles * NCHUNK * PPC / 2;
     const unsigned char *w3src = img + (PASSES == 3 ? 0u : W3H_OFF);
-    for (int g = 0; g < total; g++) {
-      const int slot = g & (NSLOT - 1);
-      mbar_wait(smem_u32(&S.free_bar[slot]), (((uint32_t)g >> L::SLOT_SHIFT) & 1u) ^ 1u);   // first round passes immediately
+    for (int gp = 0; gp < total; gp++) {
+      const int d = gp & (NPAIR - 1);
+      mbar_wait(smem_u32(&S.free_bar[d]), (((uint32_t)gp >> PAIR_SHIFT) & 1u) ^ 1u);   // first round passes immediately
       if (elect_one()) {
-        const uint32_t fb = smem_u32(&S.full_bar[slot]);
-        if ((a.exp_flags & 1) && g >= NSLOT) { mbar_arrive(fb); }
+        const uint32_t fb = smem_u32(&S.full_bar[d]);
+        if ((a.exp_flags & 1) && gp >= NPAIR) { mbar_arrive(fb); }
         else {
-          mbar_expect_tx(fb, PIECE);
-          bulk_g2s(ring_s + (uint32_t)slot * PIECE, w3src + (size_t)(g & (NCHUNK * PPC - 1)) * PIECE, PIECE, fb);
+          mbar_expect_tx(fb, 2 * PIECE);
+          bulk_g2s(ring_s + (uint32_t)d * 2 * PIECE, w3src + (size_t)(gp & (NCHUNK * PPC / 2 - 1)) * 2 * PIECE, 2 * PIECE, fb);
         }
       }
       __syncwarp();
@@ -427,10 +429,12 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
 #pragma unroll
         for (int i = 0; i < PPC; i++) {    // 3-pass pieces: W3 hi kb0, hi kb1, lo kb0, lo kb1;  2-pass: W3 kb0, kb1
           const int slot = g & (NSLOT - 1);
-          tw = clock64();
-          mbar_wait(smem_u32(&S.full_bar[slot]), (g >> L::SLOT_SHIFT) & 1u);
-          t_full += clock64() - tw;
-          tc_fence_after();
+          if ((i & 1) == 0) {   // pieces arrive in pairs
+            tw = clock64();
+            mbar_wait(smem_u32(&S.full_bar[slot >> 1]), (g >> L::SLOT_SHIFT) & 1u);
+            t_full += clock64() - tw;
+            tc_fence_after();
+          }
           const uint32_t a_s = ring_s + (uint32_t)slot * PIECE;
           const uint32_t kb = (uint32_t)(i & 1) * PIECE;
           if (elect_one()) {
@@ -455,7 +459,7 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
                 umma(d, wd, umma_desc(x3_s + kb + koff), id, 1u);                  // w_lo * x_hi
               }
             }
-            umma_commit(smem_u32(&S.free_bar[slot]));
+            if (i & 1) umma_commit(smem_u32(&S.free_bar[slot >> 1]));
             if (i == PPC - 1) {
               umma_commit(smem_u32(&S.acc_bar[buf]));
               if (c == NCHUNK - 1) umma_commit(smem_u32(&S.tile_bar));
