@@ -35,7 +35,7 @@ TRUNK_MAC_PER_PT = [6 * 64 + 64 * 128 + 128 * 1024,            # STN3d trunk
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-pts", type=int, default=1024, help="points per candidate (config_grasp.yml n_pts)")

@@ -136,14 +136,21 @@ __device__ __forceinline__ float sdf_nearest(const SdfView &s, float gx, float g
   return __ldg(s.grid + ((size_t)(int)rx * s.ny + (int)ry) * s.nz + (int)rz);
 }
 
-// true iff point x (camera frame) lies inside the posed gripper: sd(grid(inv * x)) < 0
-__device__ __forceinline__ bool point_hits(const SdfView &s, const float *inv, int mode, float x, float y, float z) {
-  const float qx = fmaf(inv[2], z, fmaf(inv[1], y, fmaf(inv[0], x, inv[9])));
-  const float qy = fmaf(inv[5], z, fmaf(inv[4], y, fmaf(inv[3], x, inv[10])));
-  const float qz = fmaf(inv[8], z, fmaf(inv[7], y, fmaf(inv[6], x, inv[11])));
-  const float gx = mul(sub(qx, s.ox), s.inv_res);   // sdf.py:252-264
-  const float gy = mul(sub(qy, s.oy), s.inv_res);
-  const float gz = mul(sub(qz, s.oz), s.inv_res);
+// camera frame -> grid coordinates of one SDF in a single affine map: G = inv_res * (inv - origin)
+// (sdf.py:252-264 folded into the inverse pose; rounding order fixed here and in oracle/filter_ref.c)
+__device__ void fold_grid(const float *inv, const SdfView &s, float *out) {
+#pragma unroll
+  for (int k = 0; k < 9; k++) out[k] = mul(inv[k], s.inv_res);
+  out[9] = mul(sub(inv[9], s.ox), s.inv_res);
+  out[10] = mul(sub(inv[10], s.oy), s.inv_res);
+  out[11] = mul(sub(inv[11], s.oz), s.inv_res);
+}
+
+// true iff point x (camera frame) lies inside the posed gripper: sd(G * x) < 0
+__device__ __forceinline__ bool point_hits(const SdfView &s, const float *G, int mode, float x, float y, float z) {
+  const float gx = fmaf(G[2], z, fmaf(G[1], y, fmaf(G[0], x, G[9])));
+  const float gy = fmaf(G[5], z, fmaf(G[4], y, fmaf(G[3], x, G[10])));
+  const float gz = fmaf(G[8], z, fmaf(G[7], y, fmaf(G[6], x, G[11])));
   if (mode == CG_SDF_TRILINEAR) {
     // Exact shortcut: a coordinate outside [0, dim-1] is clamped onto a boundary face (sdf.py:311-313) and then
     // interpolates boundary cells only; when all of those are >= 0 the result cannot be < 0, so the eight gathers
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
                                                     float *__restrict__ out_poses) {
   __shared__ float g_s[16];      // grasp_in_cam (normalised)
   __shared__ float cur_s[16];    // shifted candidate
-  __shared__ float inv_s[12];
+  __shared__ float inv_s[12], go_s[12], ge_s[12];   // inverse gripper pose; folded camera->grid maps (open, enclosed)
   __shared__ int rej_dir;
   __shared__ int flag;
   const long q = blockIdx.x;
@@ -235,12 +242,14 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
         cur[r * 4 + 3] = add(cur[r * 4 + 3], mul(mul(step, g_s[r * 4 + 1]), sign));
       mm4(cur, prm.gripper_in_grasp, gic);                     // :266
       affine_inverse(gic, inv_s);
+      fold_grid(inv_s, sdf_open, go_s);
+      fold_grid(inv_s, sdf_encl, ge_s);
       for (int e = 0; e < 16; e++) cur_s[e] = cur[e];
       flag = 0;
     }
     __syncthreads();
-    bool coll = any_point_hits(sdf_open, inv_s, prm.sdf_mode, open_pts, P1, &flag);
-    if (!coll && P2 > 0) coll = any_point_hits(sdf_encl, inv_s, prm.sdf_mode, encl_pts, P2, &flag);
+    bool coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, open_pts, P1, &flag);
+    if (!coll && P2 > 0) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts, P2, &flag);
     if (!coll) { winner = k; break; }
     __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
   }

@@ -118,13 +118,18 @@ static float sdf_nearest(const sdf_view *s, float gx, float gy, float gz, int cl
   return s->grid[((size_t)(int)rx * s->ny + (int)ry) * s->nz + (int)rz];
 }
 
-static int point_hits(const sdf_view *s, const float *inv, int mode, float x, float y, float z) {
-  const float qx = fmaf(inv[2], z, fmaf(inv[1], y, fmaf(inv[0], x, inv[9])));
-  const float qy = fmaf(inv[5], z, fmaf(inv[4], y, fmaf(inv[3], x, inv[10])));
-  const float qz = fmaf(inv[8], z, fmaf(inv[7], y, fmaf(inv[6], x, inv[11])));
-  const float gx = (qx - s->ox) * s->inv_res;
-  const float gy = (qy - s->oy) * s->inv_res;
-  const float gz = (qz - s->oz) * s->inv_res;
+static void fold_grid(const float *inv, const sdf_view *s, float *out) {
+  for (int k = 0; k < 9; k++) out[k] = inv[k] * s->inv_res;
+  out[9] = (inv[9] - s->ox) * s->inv_res;
+  out[10] = (inv[10] - s->oy) * s->inv_res;
+  out[11] = (inv[11] - s->oz) * s->inv_res;
+}
+
+/* G = camera frame -> grid coordinates ((x - origin)/res of sdf.py:252-264 folded into the inverse gripper pose) */
+static int point_hits(const sdf_view *s, const float *G, int mode, float x, float y, float z) {
+  const float gx = fmaf(G[2], z, fmaf(G[1], y, fmaf(G[0], x, G[9])));
+  const float gy = fmaf(G[5], z, fmaf(G[4], y, fmaf(G[3], x, G[10])));
+  const float gz = fmaf(G[8], z, fmaf(G[7], y, fmaf(G[6], x, G[11])));
   if (mode == 0) return sdf_trilinear(s, gx, gy, gz) < 0.f;
   int inb;
   const float sd = sdf_nearest(s, gx, gy, gz, 0, &inb);
@@ -185,13 +190,15 @@ void filter_ref(const float *nocs_pose, const float *canonical_to_nocs, const fl
     for (int k = 0; k < n_off; k++) { /* :253-287 */
       const float step = (k == 0) ? 0.f : ((k <= 2) ? step1 : step2);
       const float sign = (k == 0 || (k & 1)) ? 1.f : -1.f;
-      float gic[16], inv[12];
+      float gic[16], inv[12], go[12], ge[12];
       memcpy(cur, g, 64);
       for (int r = 0; r < 3; r++) cur[r * 4 + 3] = cur[r * 4 + 3] + (step * g[r * 4 + 1]) * sign; /* :265 */
       mm4(cur, gripper_in_grasp, gic);                                                            /* :266 */
       affine_inverse(gic, inv);
-      int coll = any_hits(&so, inv, sdf_mode, open_pts, P1);
-      if (!coll && P2 > 0) coll = any_hits(&se, inv, sdf_mode, encl_pts, P2);
+      fold_grid(inv, &so, go);
+      fold_grid(inv, &se, ge);
+      int coll = any_hits(&so, go, sdf_mode, open_pts, P1);
+      if (!coll && P2 > 0) coll = any_hits(&se, ge, sdf_mode, encl_pts, P2);
       if (!coll) { winner = k; break; }
     }
     out_status[q] = (winner >= 0) ? 0 : 3;
