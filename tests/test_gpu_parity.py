@@ -544,3 +544,25 @@ def test_my_cpp_module_surface(cuda):
     P = np.stack(poses)
     assert np.abs(np.einsum("nij,nkj->nik", P[:, :3, :3], P[:, :3, :3]) - np.eye(3)).max() < 1e-5
     assert np.allclose(P[0, :3, 3], [0.105, 0.2, 0.7], atol=1e-6) and np.allclose(P[1, :3, 3] - P[0, :3, 3], [0.003, 0, 0], atol=1e-6)
+
+
+def test_c_abi_error_codes_instead_of_exit(cuda):
+    """Bad arguments come back as CG_E* codes with a message (the reference printf+exit(1)s, collision_manager.cpp:17-27)."""
+    import ctypes as C
+    from catgrasp_b200 import _lib
+    ctx = _lib.Context.get(0)
+    lib = ctx.lib
+    h = C.c_void_p()
+    blob = np.zeros(16, np.float32)
+    assert lib.cg_net_create(ctx.h, _lib.CG_NET_CLS, 10, _lib.ptr(blob), blob.size, C.byref(h)) == _lib.CG_EINVAL
+    assert b"blob" in lib.cg_last_error(ctx.h)
+    assert lib.cg_ctx_set_engine(ctx.h, 7) == _lib.CG_EINVAL
+    x = torch.zeros((4, 3), device="cuda")
+    out = torch.zeros((4,), dtype=torch.int32, device="cuda")
+    assert lib.cg_fps_dev(ctx.h, _lib.ptr(x), 1, 0, 4, None, _lib.ptr(out)) == _lib.CG_EINVAL
+    assert lib.cg_fps_dev(ctx.h, _lib.ptr(x), 1, 100000, 4, None, _lib.ptr(out)) == _lib.CG_EINVAL      # N beyond the smem distance array
+    org = (C.c_float * 3)(0, 0, 0)
+    assert lib.cg_sdf_create(ctx.h, None, 4, 4, 4, org, C.c_float(0.001), C.byref(h)) == _lib.CG_EINVAL
+    with pytest.raises(_lib.CgError):
+        ctx.check(lib.cg_ctx_set_engine(ctx.h, -1))
+    ctx.set_engine(2)
