@@ -89,7 +89,12 @@ __global__ void __launch_bounds__(RT) ransac9d_kernel(const double *__restrict__
     double M[4][4], B[4][3], X[4][3];
     for (int i = 0; i < 4; i++) {
       const int id = ids[h * 4 + i];
-      for (int k = 0; k < 3; k++) { M[i][k] = src[(size_t)id * 3 + k]; B[i][k] = tgt[(size_t)id * 3 + k]; }
+      // cv2.estimateAffine3D (aligning.py:27) narrows its inputs to CV_32F before the double-precision solve:
+      // the four sample points go through float, the residual pass below keeps the caller's float64.
+      for (int k = 0; k < 3; k++) {
+        M[i][k] = (double)(float)src[(size_t)id * 3 + k];
+        B[i][k] = (double)(float)tgt[(size_t)id * 3 + k];
+      }
       M[i][3] = 1.0;
     }
     bool good = solve4(M, B, X);   // X[j][k]: dst_k = sum_j X[j][k] * [src,1]_j  -> A[k][j] = X[j][k]

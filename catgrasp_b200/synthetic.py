@@ -28,7 +28,7 @@ def _head_shapes(kind, n_out):
             ("conv4", (n_out, 128, 1)), ("bn1", 512), ("bn2", 256), ("bn3", 128)]
 
 
-def make_state_dict(kind, n_out, seed=0, module_prefix=True, as_torch=True):
+def make_state_dict(kind, n_out, seed=0, module_prefix=True, as_torch=True, logit_gain=1.0):
     """A PointNetCls ('cls') / PointNetSeg ('seg') state_dict with torch-default-like weight ranges
     (U(+-1/sqrt(fan_in))) and randomised BatchNorm statistics so that folding is exercised:
     running_mean ~ N(0,0.2), running_var ~ U(0.5,1.5), weight ~ U(0.5,1.5), bias ~ N(0,0.1)."""
@@ -46,6 +46,10 @@ def make_state_dict(kind, n_out, seed=0, module_prefix=True, as_torch=True):
             sd[name + ".running_mean"] = rng.normal(0, 0.2, size=(shp,)).astype(np.float32)
             sd[name + ".running_var"] = rng.uniform(0.5, 1.5, size=(shp,)).astype(np.float32)
             sd[name + ".num_batches_tracked"] = np.array(100, dtype=np.int64)
+    if logit_gain != 1.0:   # a trained head separates its classes; default-range weights give near-uniform scores
+        last = "fc3" if kind == "cls" else "conv4"
+        sd[last + ".weight"] = (sd[last + ".weight"] * logit_gain).astype(np.float32)
+        sd[last + ".bias"] = (sd[last + ".bias"] * logit_gain).astype(np.float32)
     if as_torch:
         import torch
         sd = OrderedDict((k, torch.from_numpy(np.asarray(v))) for k, v in sd.items())
@@ -54,8 +58,10 @@ def make_state_dict(kind, n_out, seed=0, module_prefix=True, as_torch=True):
     return sd
 
 
-def write_artifacts(artifact_dir, kind, n_pts, seed=0, with_normalizer=True, ce_loss_bins=100):
-    """Create an artifacts directory in the reference's layout (predicter.py:41-64, :101-132)."""
+def write_artifacts(artifact_dir, kind, n_pts, seed=0, with_normalizer=True, ce_loss_bins=100, logit_gain=1.0,
+                    state_dict=None, normalizer=None):
+    """Create an artifacts directory in the reference's layout (predicter.py:41-64, :101-132).  ``state_dict`` /
+    ``normalizer=(mean, std)`` override the seeded defaults."""
     import os
     import pickle
     import torch
@@ -72,9 +78,12 @@ def write_artifacts(artifact_dir, kind, n_pts, seed=0, with_normalizer=True, ce_
         cfg_name = "config_nunocs.yml"
     with open(os.path.join(artifact_dir, cfg_name), "w") as f:
         yaml.safe_dump(cfg, f)
-    sd = make_state_dict(kind, n_out, seed=seed)
+    sd = state_dict if state_dict is not None else make_state_dict(kind, n_out, seed=seed, logit_gain=logit_gain)
     torch.save({"epoch": 1, "state_dict": sd, "best_res": 0.0}, os.path.join(artifact_dir, "best_val.pth.tar"))
-    if with_normalizer:
+    if normalizer is not None:
+        with open(os.path.join(artifact_dir, "normalizer.pkl"), "wb") as f:
+            pickle.dump({"mean": np.asarray(normalizer[0]), "std": np.asarray(normalizer[1])}, f)
+    elif with_normalizer:
         rng = np.random.RandomState(seed + 7)
         if kind == "cls":   # grasp-frame coordinates in metres (dataset_grasp.py:84-85)
             mean = np.concatenate([rng.normal(0, 0.002, 3), rng.normal(0, 0.05, 3)])
@@ -85,6 +94,83 @@ def write_artifacts(artifact_dir, kind, n_pts, seed=0, with_normalizer=True, ce_
         with open(os.path.join(artifact_dir, "normalizer.pkl"), "wb") as f:
             pickle.dump({"mean": mean, "std": std}, f)
     return artifact_dir
+
+
+LATTICE_LEVELS = 26          # lattice positions per axis: normalised coordinate 0.04*g, NOCS bin 4*g
+_LATTICE_HINGES = LATTICE_LEVELS + 2
+
+
+def make_lattice_seg_state_dict(seed=0, mean=None, std=None, bins=100, beta=10.0, module_prefix=True, as_torch=True):
+    """A PointNetSeg state_dict that *reads the NUNOCS bins off the input*: for a cloud whose min/max-normalised
+    coordinates (augmentations.py:70-75) sit on the lattice {0, 0.04, ..., 1.0}, bin min(4*g, 99) wins with a logit gap of
+    ``beta``, so every implementation (fp32 CPU, tcgen05 split precision) yields the same NOCS cloud and the full
+    ``NunocsPredicter.predict`` success path (predicter.py:135-203) can be compared end to end.
+
+    All other weights and every BatchNorm statistic stay as random as in :func:`make_state_dict`; the hand-set
+    rows are solved *through* the random BatchNorm so folding is still exercised.  Construction: both STN heads
+    output identity (fc3 = 0); three channels carry the un-normalised coordinate through feat.conv1 / conv1 /
+    conv2; conv3 builds 28 hinges relu(x - 0.04 m) per axis; conv4 combines three hinges into a unit tent per
+    lattice level.
+    """
+    assert bins == 100 and 3 * _LATTICE_HINGES <= 128
+    sd = make_state_dict("seg", 3 * bins, seed=seed, module_prefix=False, as_torch=False)
+    eps = 1e-5
+
+    def through_bn(bn, rows, w_t, b_t):
+        """conv rows such that BN(conv(x)) = w_t @ x + b_t."""
+        s = np.sqrt(sd[bn + ".running_var"][rows].astype(np.float64) + eps) / sd[bn + ".weight"][rows]
+        w = w_t * s[:, None]
+        b = (b_t - sd[bn + ".bias"][rows]) * s + sd[bn + ".running_mean"][rows]
+        return w.astype(np.float32), b.astype(np.float32)
+
+    for stn in ("feat.stn.fc3", "feat.fstn.fc3"):
+        sd[stn + ".weight"][:] = 0
+        sd[stn + ".bias"][:] = 0
+    rows = np.arange(3)
+    # encoder conv1: channel j = input_j * std_j + mean_j (undoes the normalizer of dataset_nunocs.py:58-59)
+    w_t = np.zeros((3, 6))
+    w_t[rows, rows] = 1.0 if std is None else np.asarray(std, np.float64)[:3]
+    b_t = np.zeros(3) if mean is None else np.asarray(mean, np.float64)[:3]
+    w, b = through_bn("feat.bn1", rows, w_t, b_t)
+    sd["feat.conv1.weight"][rows] = w[:, :, None]
+    sd["feat.conv1.bias"][rows] = b
+    # head conv1 (input = [1024 global | 64 point features]) and conv2: pass the three channels on
+    for name, bn, cin, off in (("conv1", "bn1", 1088, 1024), ("conv2", "bn2", 512, 0)):
+        w_t = np.zeros((3, cin))
+        w_t[rows, off + rows] = 1.0
+        w, b = through_bn(bn, rows, w_t, np.zeros(3))
+        sd[name + ".weight"][rows] = w[:, :, None]
+        sd[name + ".bias"][rows] = b
+    # conv3: hinges h[a, m] = relu(x_a - 0.04 m), m = -1 .. LATTICE_LEVELS
+    H = _LATTICE_HINGES
+    hr = np.arange(3 * H)
+    w_t = np.zeros((3 * H, 256))
+    b_t = np.zeros(3 * H)
+    for a in range(3):
+        for i in range(H):
+            w_t[a * H + i, a] = 1.0
+            b_t[a * H + i] = -0.04 * (i - 1)
+    w, b = through_bn("bn3", hr, w_t, b_t)
+    sd["conv3.weight"][hr] = w[:, :, None]
+    sd["conv3.bias"][hr] = b
+    # conv4: tent_m = (h[m-1] - 2 h[m] + h[m+1]) / 0.04 on bin 4 m; every other bin sits at -beta
+    W4 = np.zeros((3 * bins, 128), np.float32)
+    b4 = np.full(3 * bins, -beta, np.float32)
+    for a in range(3):
+        for m in range(LATTICE_LEVELS):
+            r = a * bins + min(4 * m, bins - 1)      # x = 1.0 (the far end of the largest extent) has no bin: use 99
+            b4[r] = 0.0
+            W4[r, a * H + m] += beta / 0.04
+            W4[r, a * H + m + 1] -= 2 * beta / 0.04
+            W4[r, a * H + m + 2] += beta / 0.04
+    sd["conv4.weight"] = W4[:, :, None].copy()
+    sd["conv4.bias"] = b4
+    if as_torch:
+        import torch
+        sd = OrderedDict((k, torch.from_numpy(np.asarray(v))) for k, v in sd.items())
+    if module_prefix:
+        sd = OrderedDict(("module." + k, v) for k, v in sd.items())
+    return sd
 
 
 # ----------------------------------------------------------------------------- geometry
@@ -264,3 +350,22 @@ def make_gripper_proxy(res=0.001, pad_cells=5):
     gig = np.eye(4)
     gig[0, 3] = -0.035
     return {"open": build([palm, f1, f2]), "enclosed": build([palm, f1, f2, gap]), "gripper_in_grasp": gig}
+
+
+def sample_lattice_nut(n, seed=0, origin=(-0.012, -0.011, 0.70), spacing=0.001):
+    """A tilted hex nut snapped to a 1 mm lattice whose largest extent spans exactly LATTICE_LEVELS positions, in the
+    camera frame (z ~ 0.7 m): returns (cloud_xyz (n,3) f64, cloud_normal (n,3) f64 with float32-representable values,
+    lattice indices g (n,3) uint8).  Its min/max-normalised coordinates are 0.04*g (see make_lattice_seg_state_dict)."""
+    rng = np.random.RandomState(seed)
+    pts, nrm = sample_hex_nut(n, rng, across_flats=0.020, height=0.008, bore=0.010)
+    R = _rot_x(np.deg2rad(25.0))
+    pts = pts @ R.T
+    nrm = nrm @ R.T
+    lo = pts.min(0)
+    step = (pts.max(0) - lo).max() / (LATTICE_LEVELS - 1)
+    g = np.rint((pts - lo) / step).astype(np.int64)
+    g -= g.min(0)
+    assert g.max() == LATTICE_LEVELS - 1
+    xyz = np.asarray(origin, np.float64)[None] + spacing * g.astype(np.float64)
+    nrm = nrm.astype(np.float32).astype(np.float64)
+    return xyz, nrm, g.astype(np.uint8)

@@ -6,6 +6,8 @@ Restates aligning.py:23-119 (``estimateAffine3D``, ``estimate9DTransform_worker`
 exactly like the reference (one ``np.random.choice(len(source), 4, replace=False)`` per
 iteration, all drawn up front, aligning.py:91-97) and calls cv2.estimateAffine3D like the reference does.
 The product path is catgrasp_b200/aligning.py (CUDA hypothesis scoring); this file is its checker.
+PINNED: tests/test_host_golden.py compares it with outputs of the reference's aligning.py run here
+(tests/golden/make_golden_hostpath.py -> host_ransac9d.npz, host_nunocs_lattice.npz).
 """
 import numpy as np
 

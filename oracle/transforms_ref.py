@@ -2,8 +2,8 @@
 
 Follows dataset_grasp.py:63-91, dataset_nunocs.py:38-65, augmentations.py:70-75,
 predicter.py:67-94 and :135-150 line by line (float64 on the host, narrowed to fp32 at the
-``.float()`` of predicter.py:84/:142).  The reference modules themselves cannot be imported here
-(open3d / trimesh / autolab_core absent): parity of this file is UNPINNED.
+``.float()`` of predicter.py:84/:142).  PINNED: tests/test_host_golden.py checks this file against vectors made by
+running the reference's own predicter / dataset classes (tests/golden/make_golden_hostpath.py).
 """
 import copy
 

@@ -566,3 +566,81 @@ def test_c_abi_error_codes_instead_of_exit(cuda):
     with pytest.raises(_lib.CgError):
         ctx.check(lib.cg_ctx_set_engine(ctx.h, -1))
     ctx.set_engine(2)
+
+
+# ------------------------------------------------------------------ reference-generated host-path goldens
+# (tests/golden/make_golden_hostpath.py ran the reference's predicter.py / dataset_*.py / aligning.py to make these)
+@pytest.mark.parametrize("engine", _engines())
+def test_predict_batch_vs_reference_run(cuda, golden_dir, tmp_path, engine):
+    """GraspPredicter.predict_batch == the reference's own predict_batch on the same data, poses and numpy seed."""
+    from catgrasp_b200 import _lib
+    from catgrasp_b200.predicter import GraspPredicter
+    from catgrasp_b200.synthetic import write_artifacts
+    g = np.load(os.path.join(golden_dir, "host_predict_batch.npz"))
+    adir = write_artifacts(str(tmp_path / "artifacts-47"), "cls", n_pts=1024, seed=int(g["artifact_seed"]),
+                           logit_gain=float(g["logit_gain"]))
+    gp = GraspPredicter("nut", artifact_dir=adir)
+    _lib.Context.get(0).set_engine(engine)
+    try:
+        for tag in ("big", "small"):
+            data = {"cloud_xyz": g[f"{tag}_cloud_xyz"].astype(np.float64), "cloud_normal": g[f"{tag}_cloud_normal"].astype(np.float64)}
+            np.random.seed(0)
+            out = gp.predict_batch(data, list(g[f"{tag}_poses"]))
+            np.testing.assert_array_equal(np.random.rand(2), g[f"{tag}_next_rand"])
+            np.testing.assert_array_equal([o[0] for o in out], g[f"{tag}_labels"])
+            assert np.abs(np.stack([o[2] for o in out]) - g[f"{tag}_probs"]).max() < PROB_TOL
+            assert np.abs(np.array([o[1] for o in out]) - g[f"{tag}_conf"]).max() < PROB_TOL
+    finally:
+        _lib.Context.get(0).set_engine(2)
+
+
+def _nunocs_from_golden(g, tmp_path, sd):
+    from catgrasp_b200.predicter import NunocsPredicter
+    from catgrasp_b200.synthetic import write_artifacts
+    ndir = write_artifacts(str(tmp_path / "artifacts-78"), "seg", n_pts=8192, state_dict=sd, normalizer=(g["mean"], g["std"]))
+    return NunocsPredicter("nut", artifact_dir=ndir)
+
+
+def test_nunocs_predict_vs_reference_run_no_pose(cuda, golden_dir, tmp_path):
+    """Random weights: the reference's predict() found no pose; same subsample, same bins (up to logit ties), same
+    (None, None), same numpy-RNG consumption through transform + 2 x 10 000 RANSAC draws."""
+    from catgrasp_b200.synthetic import make_state_dict
+    g = np.load(os.path.join(golden_dir, "host_nunocs_random.npz"))
+    npred = _nunocs_from_golden(g, tmp_path, make_state_dict("seg", 300, seed=int(g["weight_seed"])))
+    data = {"cloud_xyz": g["cloud_xyz"].astype(np.float64), "cloud_normal": g["cloud_normal"].astype(np.float64)}
+    np.random.seed(0)
+    nocs, tf = npred.predict(copy.deepcopy(data))
+    assert bool(g["returned_none"]) and nocs is None and tf is None
+    np.testing.assert_array_equal(np.random.rand(2), g["next_rand"])
+    np.testing.assert_array_equal(npred.data_transformed["keep_ids"], g["keep_ids"])
+    np.testing.assert_array_equal(npred.data_transformed["input"].astype(np.float32), g["input"])
+    assert (npred.pred_bins.reshape(-1, 3) != g["nocs_bins"]).mean() < 1e-2
+
+
+def test_nunocs_predict_vs_reference_run_success_path(cuda, golden_dir, tmp_path):
+    """Lattice weights: bins identical to the reference run, and predict() returns the reference's NOCS cloud, pose,
+    best_ratio and nocs_pose (predicter.py:135-203)."""
+    from catgrasp_b200.synthetic import make_lattice_seg_state_dict
+    g = np.load(os.path.join(golden_dir, "host_nunocs_lattice.npz"))
+    npred = _nunocs_from_golden(g, tmp_path, make_lattice_seg_state_dict(seed=int(g["weight_seed"]), mean=g["mean"], std=g["std"]))
+    data = {"cloud_xyz": g["cloud_xyz"], "cloud_normal": g["cloud_normal"].astype(np.float64)}
+    np.random.seed(0)
+    nocs, tf = npred.predict(copy.deepcopy(data))
+    np.testing.assert_array_equal(np.random.rand(2), g["next_rand"])
+    np.testing.assert_array_equal(npred.data_transformed["keep_ids"], g["keep_ids"])
+    np.testing.assert_array_equal(npred.pred_bins.reshape(-1, 3), g["nocs_bins"])
+    np.testing.assert_array_equal(np.asarray(nocs, np.float32), g["nocs_cloud"])
+    assert npred.best_ratio == float(g["best_ratio"])
+    np.testing.assert_allclose(tf, g["transform"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(npred.nocs_pose, g["nocs_pose"], rtol=0, atol=1e-9)
+
+
+def test_ransac9d_vs_reference_run(cuda, golden_dir):
+    from catgrasp_b200.aligning import estimate9DTransform
+    g = np.load(os.path.join(golden_dir, "host_ransac9d.npz"))
+    np.random.seed(3)
+    tf, inl = estimate9DTransform(source=g["source"], target=g["target"], PassThreshold=0.003, max_iter=3000,
+                                  max_scale=[0.05] * 3, min_scale=[0.005, 0.005, 0.001], max_dimensions=np.array([1.2] * 3))
+    np.testing.assert_array_equal(np.random.rand(2), g["next_rand"])
+    np.testing.assert_allclose(tf, g["transform"], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(inl, g["inliers"])
