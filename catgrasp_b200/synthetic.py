@@ -369,3 +369,30 @@ def sample_lattice_nut(n, seed=0, origin=(-0.012, -0.011, 0.70), spacing=0.001):
     xyz = np.asarray(origin, np.float64)[None] + spacing * g.astype(np.float64)
     nrm = nrm.astype(np.float32).astype(np.float64)
     return xyz, nrm, g.astype(np.uint8)
+
+
+def make_filter_case(seed, G, S, scale=(1, 1, 1), n_points=2400):
+    """A sparse pile; the grasp target is object 3: its points feed the open-gripper check, all other
+    points the enclosed (swept-volume) check; the canonical frame is the target's own frame, so the
+    symmetry transforms spin the candidates about the object like Utils.py:79-84."""
+    rng = np.random.RandomState(seed)
+    scene = make_pile(n_points, n_objects=6, seed=seed)
+    obj = scene["object_id"] == 3
+    p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
+    poses = make_candidates(p1, scene["cloud_normal"][obj], G, seed=seed + 1)
+    sym = []
+    for k in range(S):                                      # nut symmetry set (Utils.py:79-84)
+        T = np.eye(4)
+        a = k * np.pi / 3
+        T[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        if k >= 6:
+            T[:3, :3] = T[:3, :3] @ np.diag([1, -1, -1])
+        sym.append(T)
+    nocs_pose = scene["object_poses"][3].copy()
+    nocs_pose[:3, :3] = nocs_pose[:3, :3] @ np.diag(scale)   # 9-DoF pose: rotation x per-axis scale
+    canonical_to_nocs = np.eye(4)
+    canonical_to_nocs[:3, 3] = rng.normal(0, 0.0005, 3)
+    inv = np.linalg.inv(nocs_pose @ canonical_to_nocs)
+    poses_can = np.stack([inv @ p for p in poses])          # canonical_to_cam * pose_can == the camera-frame pose
+    g = make_gripper_proxy()
+    return p1, p2, poses_can, np.stack(sym), nocs_pose, canonical_to_nocs, g

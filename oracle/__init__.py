@@ -10,6 +10,9 @@ Pinning status (DESIGN.md section "Oracle"):
   * transforms_ref.py, aligning_ref.py : PINNED against the reference's own predicter.py / dataset_grasp.py /
     dataset_nunocs.py / augmentations.py / aligning.py / Utils.load_model executed in the authoring container with
     the absent third-party imports stubbed (tests/golden/make_golden_hostpath.py -> tests/golden/host_*.npz).
-  * filter_ref.c                : pose logic restates my_cpp/common.cpp; the FCL/octomap geometry
-    predicate cannot be built here -> parity unpinned (SDF predicate per meshpy/sdf.py instead).
+  * filter_ref.c, occupancy_ref.c : pose logic / control flow PINNED against the reference's own my_cpp/common.cpp
+    compiled by oracle/build_ref.py into oracle/_ref (bit-identical survivor sets / occupied samples,
+    tests/golden/make_golden_mycpp.py -> tests/golden/mycpp_*.npz).  The FCL / octomap boundary cannot be built
+    here (libraries absent, versions unpinned) -> that part is parity UNPINNED; both sides use the gripper-SDF
+    predicate of meshpy/sdf.py and a restatement of the octomap calls instead (oracle/ref_shim/).
 """

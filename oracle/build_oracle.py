@@ -1,6 +1,5 @@
-"""Build recipe for the C part of the oracle (gcc only; no reference sources are compiled:
-my_cpp needs FCL + octomap + Boost which are neither vendored in /root/reference nor installed,
-so the reference's own collision code is UNBUILDABLE here -- see DESIGN.md)."""
+"""Build recipe for the C part of the oracle (gcc only; no reference sources are compiled here -- the reference's own
+my_cpp/common.cpp is compiled, with its FCL/octomap boundary shimmed, by oracle/build_ref.py into oracle/_ref/)."""
 import os
 import subprocess
 

@@ -9,6 +9,9 @@
  * (0,+),(1,+),(1,-),(2,+),(2,-); first collision-free wins; none -> zero matrix) in the fp32
  * operation order of the reference build (Eigen fixed-size products, SSE2, no FMA contraction).
  *
+ * PINNED: oracle/build_ref.py compiles the reference's common.cpp itself (Eigen 3.2.92 as vendored, -O3, SSE2); its
+ * filterGraspPose returns bit-identical survivors to this file (tests/test_mycpp_golden.py).
+ *
  * Geometry predicate: the reference calls FCL (BVH mesh vs octomap OcTree,
  * my_cpp/collision_manager.cpp:93-111); FCL and octomap are not in /root/reference nor installed,
  * so that boundary is PARITY UNPINNED.  Here, as in the CUDA kernel, the predicate is the gripper
@@ -140,6 +143,17 @@ static int any_hits(const sdf_view *s, const float *inv, int mode, const float *
   for (int p = 0; p < P; p++)
     if (point_hits(s, inv, mode, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2])) return 1;
   return 0;
+}
+
+/* The geometry predicate alone, for a given gripper pose in the camera frame (row-major 4x4): used by filter_ref below
+ * and by the oracle/_ref build of the reference's common.cpp (oracle/ref_shim/collision_manager_sdf.cpp). */
+int gripper_hits_ref(const float *gripper_in_cam, const float *grid, const int *dims, const float *origin, float res,
+                     int mode, const float *pts, int P) {
+  sdf_view s = {grid, dims[0], dims[1], dims[2], origin[0], origin[1], origin[2], 1.0f / res};
+  float inv[12], g[12];
+  affine_inverse(gripper_in_cam, inv);
+  fold_grid(inv, &s, g);
+  return any_hits(&s, g, mode, pts, P);
 }
 
 /* status: 0 accept, 1 approach-direction reject, 3 collision reject; offset: 0..4 or -1 */

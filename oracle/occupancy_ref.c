@@ -5,7 +5,8 @@
  * direction :378-380, "first occupied cell not farther than the sample" :383-393.  octomap (OcTree::insertPointCloud,
  * castRay) is not in /root/reference nor installed: the traversal below is a restatement of the SEMANTIC (occupied set
  * = cells floor(p/res) containing a scan point; 3-D DDA from the origin cell; hit reported at the cell centre) with a
- * fixed arithmetic shared with the CUDA kernel.  PARITY with octomap itself is UNPINNED.
+ * fixed arithmetic shared with the CUDA kernel.  PARITY with octomap itself is UNPINNED; the control flow is pinned:
+ * the reference's compiled function on oracle/ref_shim/octomap/octomap.h returns the same samples (tests/test_mycpp_golden.py).
  */
 #include <limits.h>
 #include <math.h>

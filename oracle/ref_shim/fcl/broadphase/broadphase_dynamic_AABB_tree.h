@@ -1,0 +1,1 @@
+#include "fcl_shim.h"

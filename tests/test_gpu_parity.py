@@ -172,31 +172,8 @@ def test_graspq_full_size_properties(cls_net):
 
 # ------------------------------------------------------------------ collision filter
 def _filter_case(seed, G, S, scale=(1, 1, 1), n_points=2400):
-    """A sparse pile; the grasp target is object 3: its points feed the open-gripper check, all other
-    points the enclosed (swept-volume) check; the canonical frame is the target's own frame, so the
-    symmetry transforms spin the candidates about the object like Utils.py:79-84."""
-    from catgrasp_b200.synthetic import make_candidates, make_gripper_proxy, make_pile
-    rng = np.random.RandomState(seed)
-    scene = make_pile(n_points, n_objects=6, seed=seed)
-    obj = scene["object_id"] == 3
-    p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
-    poses = make_candidates(p1, scene["cloud_normal"][obj], G, seed=seed + 1)
-    sym = []
-    for k in range(S):                                      # nut symmetry set (Utils.py:79-84)
-        T = np.eye(4)
-        a = k * np.pi / 3
-        T[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
-        if k >= 6:
-            T[:3, :3] = T[:3, :3] @ np.diag([1, -1, -1])
-        sym.append(T)
-    nocs_pose = scene["object_poses"][3].copy()
-    nocs_pose[:3, :3] = nocs_pose[:3, :3] @ np.diag(scale)   # 9-DoF pose: rotation x per-axis scale
-    canonical_to_nocs = np.eye(4)
-    canonical_to_nocs[:3, 3] = rng.normal(0, 0.0005, 3)
-    inv = np.linalg.inv(nocs_pose @ canonical_to_nocs)
-    poses_can = np.stack([inv @ p for p in poses])          # canonical_to_cam * pose_can == the camera-frame pose
-    g = make_gripper_proxy()
-    return p1, p2, poses_can, np.stack(sym), nocs_pose, canonical_to_nocs, g
+    from catgrasp_b200.synthetic import make_filter_case
+    return make_filter_case(seed, G, S, scale, n_points)
 
 
 @pytest.mark.parametrize("mode", [0, 1])
@@ -644,3 +621,50 @@ def test_ransac9d_vs_reference_run(cuda, golden_dir):
     np.testing.assert_array_equal(np.random.rand(2), g["next_rand"])
     np.testing.assert_allclose(tf, g["transform"], rtol=0, atol=1e-9)
     np.testing.assert_array_equal(inl, g["inliers"])
+
+
+# ------------------------------------------------------------------ goldens from the compiled reference my_cpp (oracle/build_ref.py)
+def _mk():
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_mycpp as mk
+    return mk
+
+
+@pytest.mark.parametrize("k", range(12))
+def test_filterGraspPose_equals_reference_build(cuda, golden_dir, k):
+    """my_cpp.filterGraspPose (20 positional args, survivors only) returns exactly the survivor set the reference's own
+    compiled filterGraspPose returned (pose logic = reference code, geometry predicate = gripper SDF on both sides)."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from oracle import mycpp_ref
+    mk = _mk()
+    g_ = np.load(os.path.join(golden_dir, "mycpp_filter.npz"))
+    S, scale, mode, adjust, fdir = mk.FILTER_CASES[k]
+    (p1, p2, poses, sym, nocs_pose, c2n, g), dg = mk.filter_inputs(S, scale)
+    assert np.array_equal(dg, g_[f"inputs_sha_{k}"])
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    my_cpp.register_gripper_sdf(g["open"]["V"], g["open"]["F"], so)
+    my_cpp.register_gripper_sdf(g["enclosed"]["V"], g["enclosed"]["F"], se)
+    old = my_cpp.DEFAULT_SDF_MODE
+    my_cpp.DEFAULT_SDF_MODE = mode
+    try:
+        res = my_cpp.filterGraspPose(list(poses), list(sym), nocs_pose, c2n, np.eye(4), np.eye(4), g["gripper_in_grasp"],
+                                     fdir, False, adjust, [3] * 7, [-3] * 7, g["open"]["V"], g["open"]["F"],
+                                     g["enclosed"]["V"], g["enclosed"]["F"], p1, p2, 0.0005, False)
+    finally:
+        my_cpp.DEFAULT_SDF_MODE = old
+    assert np.array_equal(mycpp_ref.sort_poses(np.stack(res)).view(np.uint32), g_[f"survivors_{k}"])
+
+
+@pytest.mark.parametrize("k", range(3))
+def test_occupancy_equals_reference_build(cuda, golden_dir, k):
+    from catgrasp_b200 import my_cpp
+    mk = _mk()
+    g_ = np.load(os.path.join(golden_dir, "mycpp_occupancy.npz"))
+    res, n, seed = mk.OCC_CASES[k]
+    pts = mk.occupancy_inputs(n, seed)
+    assert np.array_equal(mk.digest(pts), g_[f"inputs_sha_{k}"])
+    out = my_cpp.makeOccupancyGridFromCloudScan(pts, np.eye(3), res)
+    assert np.array_equal(np.unique(out.view(np.uint32), axis=0), g_[f"points_{k}"])

@@ -1,0 +1,56 @@
+"""CPU: pin the C oracle (filter_ref.c, occupancy_ref.c) and the host helpers against outputs of the reference's own
+my_cpp/common.cpp as compiled by oracle/build_ref.py (tests/golden/make_golden_mycpp.py wrote the fixtures; the
+FCL / octomap boundary of that build is shimmed, see oracle/build_ref.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_golden_mycpp as mk  # noqa: E402  (case tables + input builders shared with the generator)
+
+from oracle import filter_ref, mycpp_ref  # noqa: E402
+
+
+@pytest.mark.parametrize("k", range(len(mk.FILTER_CASES)))
+def test_filter_oracle_equals_reference_build(golden_dir, k):
+    g_ = np.load(os.path.join(golden_dir, "mycpp_filter.npz"))
+    S, scale, mode, adjust, fdir = mk.FILTER_CASES[k]
+    (p1, p2, poses, sym, nocs_pose, c2n, g), dg = mk.filter_inputs(S, scale)
+    assert np.array_equal(dg, g_[f"inputs_sha_{k}"]), "synthetic inputs drifted: regenerate the fixture"
+    st, off, out = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
+                                         g["enclosed"], p2)
+    mine = mycpp_ref.sort_poses(out[st == 0]).view(np.uint32)
+    assert np.array_equal(mine, g_[f"survivors_{k}"])          # same survivors, bit for bit (poses include the winning offset)
+
+
+@pytest.mark.parametrize("k", range(len(mk.OCC_CASES)))
+def test_occupancy_oracle_equals_reference_build(golden_dir, k):
+    g_ = np.load(os.path.join(golden_dir, "mycpp_occupancy.npz"))
+    res, n, seed = mk.OCC_CASES[k]
+    pts = mk.occupancy_inputs(n, seed)
+    assert np.array_equal(mk.digest(pts), g_[f"inputs_sha_{k}"])
+    flags, org, dims = filter_ref.occupancy_ref(pts, res)
+    idx = np.argwhere(flags > 0)
+    mine = (org[None, :] + idx.astype(np.float32) * np.float32(res)).astype(np.float32)
+    assert np.array_equal(np.unique(mine.view(np.uint32), axis=0), g_[f"points_{k}"])
+
+
+def test_direction_vec_to_rotation_matches_reference_build(golden_dir):
+    from catgrasp_b200.my_cpp import directionVecToRotation
+    g_ = np.load(os.path.join(golden_dir, "mycpp_direction.npz"))
+    for d, R in zip(g_["direction"], g_["R"]):
+        np.testing.assert_allclose(directionVecToRotation(d, g_["ref"]), R, rtol=0, atol=5e-6)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/my_cpp/common.cpp"), reason="needs the reference sources")
+def test_ref_build_recipe_reproduces_fixture(golden_dir):
+    """Where the reference is present the recipe itself is exercised: build oracle/_ref and re-run one case live."""
+    g_ = np.load(os.path.join(golden_dir, "mycpp_filter.npz"))
+    k = 6
+    S, scale, mode, adjust, fdir = mk.FILTER_CASES[k]
+    (p1, p2, poses, sym, nocs_pose, c2n, g), _ = mk.filter_inputs(S, scale)
+    ref = mycpp_ref.filterGraspPose(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
+                                    g["enclosed"], p2)
+    assert np.array_equal(mycpp_ref.sort_poses(ref).view(np.uint32), g_[f"survivors_{k}"])
