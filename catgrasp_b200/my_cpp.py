@@ -102,6 +102,33 @@ def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_noc
     return status, offset, poses
 
 
+def _mm4_f32(A, B):
+    """(...,4,4) x (...,4,4) in float32 with the accumulation order of the reference build's Eigen fixed-size product
+    (sum over k = 0..3, one rounding per multiply and per add; my_cpp is built without FMA, CMakeLists.txt:5-6) --
+    the same order as the CUDA kernel (csrc/cg_collide.cu) and oracle/filter_ref.c."""
+    A = np.asarray(A, np.float32)
+    B = np.asarray(B, np.float32)
+    out = (A[..., :, 0:1] * B[..., 0:1, :]).astype(np.float32)
+    for k in (1, 2, 3):
+        out = (out + (A[..., :, k:k + 1] * B[..., k:k + 1, :]).astype(np.float32)).astype(np.float32)
+    return out
+
+
+def grasp_in_cam_unshifted(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform):
+    """common.cpp:159,190-197 on the host, bit-identical to the kernel: canonical_to_cam * (tf_j * pose_i) with the
+    first three columns normalised, for every (i, j) -> (G*S, 4, 4) float32.  This is the pose the reference hands to
+    the approach-direction and IK tests (:199-226), before any lateral offset."""
+    f = lambda m: np.asarray(m, np.float64).astype(np.float32)      # noqa: E731  pybind narrows float64 -> float32
+    gp = f(grasp_poses).reshape(-1, 1, 4, 4)
+    st = f(symmetry_tfs).reshape(1, -1, 4, 4)
+    c2c = _mm4_f32(f(nocs_pose), f(canonical_to_nocs_transform))
+    g = _mm4_f32(c2c, _mm4_f32(st, gp)).reshape(-1, 4, 4)
+    x, y, z = g[:, 0, :3], g[:, 1, :3], g[:, 2, :3]
+    n = np.sqrt(((x * x).astype(np.float32) + (y * y).astype(np.float32)).astype(np.float32) + (z * z).astype(np.float32))
+    g[:, :3, :3] = (g[:, :3, :3] / n[:, None, :]).astype(np.float32)
+    return g
+
+
 def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform, cam_in_world, ee_in_grasp,
                     gripper_in_grasp, filter_approach_dir_face_camera, filter_ik, adjust_collision_pose, upper, lower,
                     gripper_vertices, gripper_faces, gripper_enclosed_vertices, gripper_enclosed_faces,
@@ -129,14 +156,12 @@ def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_tran
     if filter_ik:
         # common.cpp:214-226: IK is evaluated on the UN-shifted grasp_in_cam; the approach / IK / collision
         # tests are independent rejections, so running IK on the collision survivors keeps the same set.
-        S = len(symmetry_tfs)
         cam = np.asarray(cam_in_world, np.float64).astype(np.float32)
         eeg = np.asarray(ee_in_grasp, np.float64).astype(np.float32)
-        shifts = np.array([0.0, 0.001, -0.001, 0.002, -0.002], np.float32)
+        unshifted = grasp_in_cam_unshifted(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform)
         for q in np.nonzero(keep)[0]:
-            g = poses[q].copy()
-            g[:3, 3] -= shifts[offset[q]] * g[:3, 1]
-            if not _IK_SOLVER(cam @ g @ eeg, upper, lower):
+            ee_in_base = _mm4_f32(_mm4_f32(cam, unshifted[q]), eeg)      # common.cpp:216, left to right
+            if not _IK_SOLVER(ee_in_base, upper, lower):
                 keep[q] = False
                 n_ik += 1
     if verbose:

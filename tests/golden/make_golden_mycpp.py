@@ -42,6 +42,22 @@ def filter_inputs(S, scale):
     return (p1, p2, poses, sym, nocs_pose, c2n, g), dg
 
 
+# filter_ik=True cases (common.cpp:214-226) run the reference's generated KUKA iiwa14 ikfast solver, compiled into oracle/_ref
+IK_CASES = [(12, (1.0, 1.1, 0.9), 0, True, True), (1, (1, 1, 1), 1, False, False)]
+IK_UPPER = np.deg2rad([170, 120, 170, 120, 170, 120, 175])
+IK_LOWER = -IK_UPPER
+
+
+def ik_frames():
+    cam_in_world = np.eye(4)
+    cam_in_world[:3, :3] = np.diag([1.0, -1.0, -1.0])            # camera looks down at the bin
+    cam_in_world[:3, 3] = [0.6, 0.0, 0.85]
+    ee_in_grasp = np.eye(4)
+    ee_in_grasp[:3, :3] = np.array([[0, 0, 1], [0, 1, 0], [-1, 0, 0]], float).T
+    ee_in_grasp[:3, 3] = [-0.17, 0, 0]
+    return cam_in_world, ee_in_grasp
+
+
 def occupancy_inputs(n, seed):
     sc = synthetic.make_pile(n, n_objects=4, seed=seed)
     return sc["cloud_xyz"].astype(np.float32)
@@ -59,6 +75,15 @@ def main():
         out[f"survivors_{k}"] = mycpp_ref.sort_poses(ref).view(np.uint32)
         out[f"inputs_sha_{k}"] = dg
         print("filter case", k, (S, scale, mode, adjust, fdir), "survivors", len(ref))
+    cam, ee = ik_frames()
+    for k, (S, scale, mode, adjust, fdir) in enumerate(IK_CASES):
+        (p1, p2, poses, sym, nocs_pose, c2n, g), dg = filter_inputs(S, scale)
+        ref = mycpp_ref.filterGraspPose(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
+                                        g["enclosed"], p2, cam_in_world=cam, ee_in_grasp=ee, filter_ik=True,
+                                        upper=IK_UPPER, lower=IK_LOWER)
+        out[f"ik_survivors_{k}"] = mycpp_ref.sort_poses(ref).view(np.uint32)
+        out[f"ik_inputs_sha_{k}"] = digest(dg, cam, ee, IK_UPPER, IK_LOWER)
+        print("filter+IK case", k, (S, scale, mode, adjust, fdir), "survivors", len(ref))
     np.savez_compressed(os.path.join(HERE, "mycpp_filter.npz"), **out)
     out = {}
     for k, (res, n, seed) in enumerate(OCC_CASES):

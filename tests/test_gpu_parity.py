@@ -668,3 +668,33 @@ def test_occupancy_equals_reference_build(cuda, golden_dir, k):
     assert np.array_equal(mk.digest(pts), g_[f"inputs_sha_{k}"])
     out = my_cpp.makeOccupancyGridFromCloudScan(pts, np.eye(3), res)
     assert np.array_equal(np.unique(out.view(np.uint32), axis=0), g_[f"points_{k}"])
+
+
+@pytest.mark.parametrize("k", range(2))
+def test_filterGraspPose_with_ik_equals_reference_build(cuda, golden_dir, k):
+    """filter_ik=True through the 20-argument call, the IK hook being the reference's own ikfast solver (oracle/_ref)."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from oracle import mycpp_ref
+    if not mycpp_ref.available():
+        pytest.skip("oracle/_ref (reference ikfast build) not present")
+    mk = _mk()
+    g_ = np.load(os.path.join(golden_dir, "mycpp_filter.npz"))
+    S, scale, mode, adjust, fdir = mk.IK_CASES[k]
+    (p1, p2, poses, sym, nocs_pose, c2n, g), dg = mk.filter_inputs(S, scale)
+    cam, ee = mk.ik_frames()
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    my_cpp.register_gripper_sdf(g["open"]["V"], g["open"]["F"], so)
+    my_cpp.register_gripper_sdf(g["enclosed"]["V"], g["enclosed"]["F"], se)
+    old = my_cpp.DEFAULT_SDF_MODE
+    my_cpp.DEFAULT_SDF_MODE = mode
+    my_cpp.set_ik_solver(lambda ee_in_base, upper, lower: mycpp_ref.ik_solution_count(ee_in_base, upper, lower) > 0)
+    try:
+        res = my_cpp.filterGraspPose(list(poses), list(sym), nocs_pose, c2n, cam, ee, g["gripper_in_grasp"], fdir, True, adjust,
+                                     list(mk.IK_UPPER), list(mk.IK_LOWER), g["open"]["V"], g["open"]["F"], g["enclosed"]["V"],
+                                     g["enclosed"]["F"], p1, p2, 0.0005, False)
+    finally:
+        my_cpp.DEFAULT_SDF_MODE = old
+        my_cpp.set_ik_solver(None)
+    assert np.array_equal(mycpp_ref.sort_poses(np.stack(res)).view(np.uint32), g_[f"ik_survivors_{k}"])

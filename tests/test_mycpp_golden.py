@@ -54,3 +54,24 @@ def test_ref_build_recipe_reproduces_fixture(golden_dir):
     ref = mycpp_ref.filterGraspPose(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
                                     g["enclosed"], p2)
     assert np.array_equal(mycpp_ref.sort_poses(ref).view(np.uint32), g_[f"survivors_{k}"])
+
+
+@pytest.mark.skipif(not mycpp_ref.available(), reason="needs oracle/_ref (the reference's ikfast solver)")
+@pytest.mark.parametrize("k", range(len(mk.IK_CASES)))
+def test_filter_with_ik_stage_equals_reference_build(golden_dir, k):
+    """filter_ik=True: oracle survivors, thinned by the reference's own get_ik_within_limits on the un-shifted pose
+    (catgrasp_b200.my_cpp.grasp_in_cam_unshifted, bit-identical to the kernel), equal the reference's survivors."""
+    from catgrasp_b200.my_cpp import _mm4_f32, grasp_in_cam_unshifted
+    g_ = np.load(os.path.join(golden_dir, "mycpp_filter.npz"))
+    S, scale, mode, adjust, fdir = mk.IK_CASES[k]
+    (p1, p2, poses, sym, nocs_pose, c2n, g), dg = mk.filter_inputs(S, scale)
+    cam, ee = mk.ik_frames()
+    assert np.array_equal(mk.digest(dg, cam, ee, mk.IK_UPPER, mk.IK_LOWER), g_[f"ik_inputs_sha_{k}"])
+    st, off, out = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
+                                         g["enclosed"], p2)
+    u = grasp_in_cam_unshifted(poses, sym, nocs_pose, c2n)
+    f = lambda m: np.asarray(m, np.float64).astype(np.float32)      # noqa: E731
+    keep = [q for q in np.nonzero(st == 0)[0]
+            if mycpp_ref.ik_solution_count(_mm4_f32(_mm4_f32(f(cam), u[q]), f(ee)), mk.IK_UPPER, mk.IK_LOWER) > 0]
+    assert 0 < len(keep) < int((st == 0).sum())
+    assert np.array_equal(mycpp_ref.sort_poses(out[keep]).view(np.uint32), g_[f"ik_survivors_{k}"])
