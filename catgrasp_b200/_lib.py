@@ -67,6 +67,8 @@ SIGNATURES = {
     "cg_occupancy_grid_geometry": (_i, [_vp, _i, _f, C.POINTER(_i), C.POINTER(_f)]),
     "cg_occupancy_from_scan_host": (_i, [_vp, _vp, _i, _f, _vp]),
     "cg_ransac9d_host": (_i, [_vp, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cg_cone_poses_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_double, _vp, _vp]),
+    "cg_center_grasps_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
     "cg_square_distance_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_index_points_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cg_fps_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

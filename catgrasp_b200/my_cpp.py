@@ -72,7 +72,7 @@ def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_noc
     if isinstance(grasp_poses, torch.Tensor) and grasp_poses.is_cuda:
         dev = grasp_poses.device
         gp = grasp_poses.to(torch.float32).contiguous().reshape(-1, 16)
-        st = torch.as_tensor(symmetry_tfs).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 16)
+        st = torch.as_tensor(np.asarray(symmetry_tfs)).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 16)
         p1 = torch.as_tensor(open_pts).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 3)
         p2 = torch.as_tensor(enclosed_pts).to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 3)
         G, S = gp.shape[0], st.shape[0]

@@ -203,6 +203,21 @@ int cg_ransac9d_host(cg_ctx *ctx, const double *source, const double *target, in
                      double pass_threshold, const double min_scale[3], const double max_scale[3],
                      const double *max_dims, double *out_ratio, double *out_T, unsigned char *out_valid);
 
+/* ---- Cone pose enumeration (device pointers, float64 like the reference's numpy) ----------
+ * Replaces: dexnet/grasping/grasp_sampler.py:266-286 (PointConeGraspSampler.sample_one_surface_point: the
+ *   R0 / R0 @ R_sphere @ R_inplane x approach-depth loops, Utils.py:172-179 normalizeRotation) and :191-203
+ *   (center_ob_between_gripper).  Its C++ twin my_cpp/common.cpp:111-153 (augmentGraspPoses) is uncalled.
+ *   surface_pts (S,3), R0 (S,9 row-major: columns approach / major / minor, computed on the host, :262),
+ *   R_sphere (NS,9), R_inplane (NI,9), depths (ND) = np.arange(0, hand_depth, approach_step)
+ *   out_poses64 (P,16) row-major 4x4, P = S * (1 + NS*NI) * ND, ordered (surface point, rotation, depth) like the
+ *   reference's list; out_poses32 (P,16) or NULL = the same poses narrowed to float32 for cg_filter_grasp_pose_dev.   */
+int cg_cone_poses_dev(cg_ctx *ctx, const double *surface_pts, const double *R0, int S, const double *R_sphere, int NS,
+                      const double *R_inplane, int NI, const double *depths, int ND, double init_bite,
+                      double *out_poses64, float *out_poses32);
+/* grasp_sampler.py:191-203: shift every pose along its y axis to the middle of the object's extent (pts (M,3) float64,
+ * camera frame) in the grasp frame; poses are updated in place (poses32 may be NULL).                                */
+int cg_center_grasps_dev(cg_ctx *ctx, double *poses64, float *poses32, int P, const double *pts, int M);
+
 /* ---- PointNet++ primitives (device pointers) ---------------------------
  * Replace the free functions of pointnet2.py:14-149.  Indices are int32 on
  * the device (the Python mirror widens to int64 like the reference).        */

@@ -38,4 +38,18 @@ T = np.eye(4); T[:3, :3] *= 0.02; T[:3, 3] = [0, 0, 0.7]
 tgt = (T @ np.c_[src, np.ones(8192)].T).T[:, :3] + rng.normal(0, 0.0004, (8192, 3))
 np.random.seed(0)
 t = time.perf_counter(); estimate9DTransform(src, tgt, 0.003, max_iter=10000, max_scale=[0.05] * 3, min_scale=[0.005] * 3, max_dimensions=np.array([1.2] * 3)); out["ransac_10000x8192_total_ms"] = (time.perf_counter() - t) * 1e3
+# K5-scale cone enumeration: ~1M poses, centred on a 10k-point object
+from catgrasp_b200 import grasp_sampler as gs
+rng = np.random.RandomState(0)
+S = 1024
+surf = rng.uniform(-0.01, 0.01, (S, 3)) + [0, 0, 0.7]
+R0s = np.stack([np.linalg.qr(rng.normal(size=(3, 3)))[0] for _ in range(S)])
+sph = gs.cone_sphere_points(30)
+obj = rng.uniform(-0.01, 0.01, (10000, 3)) + [0, 0, 0.7]
+def run():
+    return gs.enumerate_poses(surf, R0s, sph, 0.03, 0.005, 0.002, points_for_center=obj)
+p64, p32 = run(); torch.cuda.synchronize()
+out["cone_poses"] = int(p64.shape[0])
+out["cone_enumerate_center_10k_ms"] = timeit(run, n=5)
+out["cone_enumerate_only_ms"] = timeit(lambda: gs.enumerate_poses(surf, R0s, sph, 0.03, 0.005, 0.002), n=5)
 print(json.dumps(out))

@@ -698,3 +698,48 @@ def test_filterGraspPose_with_ik_equals_reference_build(cuda, golden_dir, k):
         my_cpp.DEFAULT_SDF_MODE = old
         my_cpp.set_ik_solver(None)
     assert np.array_equal(mycpp_ref.sort_poses(np.stack(res)).view(np.uint32), g_[f"ik_survivors_{k}"])
+
+
+# ------------------------------------------------------------------ cone pose enumeration (grasp_sampler.py:131-298), SURVEY 8f F3
+@pytest.mark.parametrize("k", range(2))
+def test_cone_grasp_poses_vs_reference_run(cuda, golden_dir, k):
+    """cone_grasp_poses == the poses the reference's own PointConeGraspSampler.sample_grasps handed to filterGraspPose
+    (tests/golden/make_golden_cone.py), same numpy-RNG consumption; float64 to 1e-13, float32 copy = narrowed values."""
+    import test_cone_golden as tc
+    from catgrasp_b200 import grasp_sampler as gs
+    g = np.load(os.path.join(golden_dir, "cone_poses.npz"))
+    c = tc.CASES[k]
+    pts, nrm = tc.case_inputs(c)
+    np.random.seed(7)
+    p64, p32 = gs.cone_grasp_poses(pts, nrm, tc.HAND_DEPTH, tc.INIT_BITE, max_num_samples=c["max_num_samples"],
+                                   n_sphere_dir=c["n_sphere_dir"], approach_step=c["approach_step"],
+                                   center_ob_between_gripper=c["center"])
+    np.testing.assert_array_equal(np.random.rand(2), g[f"next_rand_{k}"])
+    ref = g[f"poses_{k}"]
+    assert tuple(p64.shape) == ref.shape and p64.is_cuda and p32.dtype == torch.float32
+    assert np.abs(p64.cpu().numpy() - ref).max() < 1e-13
+    assert np.abs(p32.cpu().numpy().astype(np.float64) - ref.astype(np.float32)).max() < 1.3e-7   # <= 1 ulp at |x| < 1
+
+
+def test_cone_poses_feed_filter_on_device(cuda):
+    """The device-resident float32 poses go straight into the collision filter and give the same verdicts as the same
+    poses passed from the host (the reference's route: list of numpy 4x4 -> pybind -> float32)."""
+    from catgrasp_b200 import grasp_sampler as gs, my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_gripper_proxy, make_pile
+    scene = make_pile(2400, n_objects=6, seed=43)
+    obj = scene["object_id"] == 3
+    p1, p2 = scene["cloud_xyz"][obj], scene["cloud_xyz"][~obj]
+    np.random.seed(1)
+    p64, p32 = gs.cone_grasp_poses(p1.copy(), scene["cloud_normal"][obj].copy(), 0.012, 0.002, max_num_samples=12,
+                                   n_sphere_dir=6, approach_step=0.004)
+    g = make_gripper_proxy()
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    eye = np.eye(4)
+    dst, doff, dout = my_cpp.filter_grasp_pose_raw(p32, [eye], eye, eye, g["gripper_in_grasp"], True, True, so, p1, se, p2)
+    hst, hoff, hout = my_cpp.filter_grasp_pose_raw(p64.cpu().numpy(), [eye], eye, eye, g["gripper_in_grasp"], True, True, so,
+                                                   p1, se, p2)
+    assert np.array_equal(dst.cpu().numpy(), hst) and np.array_equal(doff.cpu().numpy(), hoff)
+    assert np.array_equal(dout.cpu().numpy().view(np.uint32), hout.view(np.uint32))
+    assert p32.shape[0] > 0 and p32.shape[0] % ((1 + 6 * 6) * 3) == 0 and (hst == 0).any() and (hst != 0).any()
