@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--engine", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 3-pass bf16, 2 tcgen05 2-pass fp16 (default: library default)")
     ap.add_argument("--cpu-sample", type=int, default=192, help="candidates in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap", action="store_true",
+                    help="run the collision filter concurrently with the networks on a second library context / stream "
+                         "(measured: +1.6 %% throughput, but the trunk launches it shares SMs with get 2.6 %% slower)")
     return ap.parse_args()
 
 
@@ -206,7 +209,9 @@ def workload_config(args):
                         f"n_pts={args.n_pts} per candidate, grasp-Q PointNetCls + SDF collision (5 lateral offsets, "
                         f"trilinear) + 1 NUNOCS PointNetSeg forward ({args.nunocs_pts} pts) per step",
             "candidates_per_gpu": args.candidates, "scene_pts": args.scene_pts, "n_pts": args.n_pts,
-            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"candidate-shard x{args.gpus}"}
+            "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"candidate-shard x{args.gpus}",
+            "streams": ("networks and collision filter on two library contexts (two streams), joined every step"
+                        if getattr(args, "overlap", False) else "single stream")}
 
 
 def main():
@@ -239,8 +244,12 @@ def main():
     if args.engine is not None:
         ctx.set_engine(args.engine)
     g = wl["gripper"]
-    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"], device=local)
-    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"], device=local)
+    # With --overlap the collision filter gets a library context of its own (own stream + workspace): it is independent
+    # of the network half of the step, so it can run concurrently on a lower-priority stream and fill the SMs the small
+    # FC / per-object launches leave idle; both halves are joined at the end of every step.  Default: back to back.
+    ctx_f = _lib.Context(local) if args.overlap else ctx
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"], device=local, ctx=ctx_f)
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"], device=local, ctx=ctx_f)
     B, N, M = args.candidates, args.n_pts, args.scene_pts
     scene = wl["scene"]
 
@@ -258,11 +267,27 @@ def main():
     eye = np.eye(4)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    s_net = torch.cuda.Stream(device=dev, priority=-1) if args.overlap else None
+    s_flt = torch.cuda.Stream(device=dev, priority=0) if args.overlap else None
+
     def step_device():
-        coords, conf, _ = seg.nunocs_dev(d_nun, 100)
-        probs, label = cls.graspq_dev(d_xyz, d_nrm, d_pose, d_ids, d_mean, d_std)
-        st, off, poses = my_cpp.filter_grasp_pose_raw(d_pose32, eye[None], eye, eye, g["gripper_in_grasp"], True, True,
-                                                      so, d_open, se, d_bg)
+        if args.overlap:
+            cur = torch.cuda.current_stream()
+            s_net.wait_stream(cur)
+            s_flt.wait_stream(cur)
+            with torch.cuda.stream(s_net):
+                coords, conf, _ = seg.nunocs_dev(d_nun, 100)
+                probs, label = cls.graspq_dev(d_xyz, d_nrm, d_pose, d_ids, d_mean, d_std)
+            with torch.cuda.stream(s_flt):
+                st, off, poses = my_cpp.filter_grasp_pose_raw(d_pose32, eye[None], eye, eye, g["gripper_in_grasp"], True,
+                                                              True, so, d_open, se, d_bg)
+            cur.wait_stream(s_net)
+            cur.wait_stream(s_flt)
+        else:
+            coords, conf, _ = seg.nunocs_dev(d_nun, 100)
+            probs, label = cls.graspq_dev(d_xyz, d_nrm, d_pose, d_ids, d_mean, d_std)
+            st, off, poses = my_cpp.filter_grasp_pose_raw(d_pose32, eye[None], eye, eye, g["gripper_in_grasp"], True, True,
+                                                          so, d_open, se, d_bg)
         rec = pack_records(probs, st, off)
         if world > 1:
             rec = all_gather_records(rec, B * world)     # every rank holds a full block: one ncclAllGather
@@ -281,6 +306,7 @@ def main():
     if rank == 0:
         sampler.start()
     ctx.reset_launch_count()
+    ctx_f.reset_launch_count()
     ctx.profile(True)
     ctx.profile_read()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,7 +318,7 @@ def main():
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = ctx.launch_count()
+    launches = ctx.launch_count() + (ctx_f.launch_count() if ctx_f is not ctx else 0)
     trunk_ms, trunk_n = ctx.profile_read()
     ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -349,13 +375,33 @@ def main():
     lib = ctx.lib
     P = _lib.ptr
 
-    def step_host():
+    def net_host():
         ctx.check(lib.cg_nunocs_forward_host(seg.h, P(h["nun"]), args.nunocs_pts, 100, P(o_coords), P(o_conf), P(o_bins)))
         ctx.check(lib.cg_graspq_forward_host(cls.h, P(h["xyz"]), P(h["nrm"]), M, P(h["pose"]), B, P(h["ids"]), N,
                                              P(h["mean"]), P(h["std"]), P(o_probs), P(o_label)))
-        ctx.check(lib.cg_filter_grasp_pose_host(ctx.h, C.byref(prm), P(h["pose32"]), B, P(sym), 1, so.h, P(h["open"]),
-                                                h["open"].shape[0], se.h, P(h["bg"]), h["bg"].shape[0], P(o_st),
-                                                P(o_off), P(o_poses)))
+
+    def flt_host():
+        ctx_f.check(lib.cg_filter_grasp_pose_host(ctx_f.h, C.byref(prm), P(h["pose32"]), B, P(sym), 1, so.h, P(h["open"]),
+                                                  h["open"].shape[0], se.h, P(h["bg"]), h["bg"].shape[0], P(o_st),
+                                                  P(o_off), P(o_poses)))
+
+    # the blocking *_host entry points run on each context's own (non-blocking) stream; with --overlap the filter call is
+    # issued from a second host thread (ctypes releases the GIL), exactly what a caller with two contexts would do
+    ctx.check(lib.cg_ctx_use_own_stream(ctx.h))
+    ctx_f.check(lib.cg_ctx_use_own_stream(ctx_f.h))
+    pool = None
+    if args.overlap:
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)
+
+    def step_host():
+        if pool is not None:
+            fut = pool.submit(flt_host)
+            net_host()
+            fut.result()
+        else:
+            net_host()
+            flt_host()
 
     h2d = sum(h[k].numel() * h[k].element_size() for k in ("xyz", "nrm", "pose", "ids", "mean", "std", "nun", "pose32",
                                                            "open", "bg")) + 64

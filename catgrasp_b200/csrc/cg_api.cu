@@ -1,5 +1,6 @@
 // cg_api.cu -- context management for the C ABI (include/catgrasp_b200.h).
 #include "cg_common.cuh"
+#include <stdlib.h>
 
 extern "C" const char *cg_version(void) { return "catgrasp_b200 0.1 (sm_100a)"; }
 
@@ -19,6 +20,8 @@ extern "C" int cg_ctx_create(int device, cg_ctx **out) {
   cg_ctx *ctx = new cg_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
+  const char *tr = getenv("CG_TRACE");
+  ctx->trace = tr && tr[0] == '1';
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return CG_ECUDA;
@@ -99,6 +102,33 @@ static int grow(cg_ctx *ctx, void **p, size_t *cur, size_t bytes, bool host) {
 int cg_ws_reserve(cg_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, false); }
 int cg_io_reserve(cg_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->io, &ctx->io_bytes, bytes, false); }
 int cg_hs_reserve(cg_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->hs, &ctx->hs_bytes, bytes, true); }
+
+// CG_TRACE diagnostics: durations between consecutive post-launch events on the context's stream, grouped by call site
+void cg_trace_mark(cg_ctx *ctx, const char *where) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, ctx->stream);
+  ctx->trace_events.emplace_back(where, e);
+  if (ctx->trace_events.size() < 3000) return;
+  cudaEventSynchronize(e);
+  std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+  for (size_t i = 1; i < ctx->trace_events.size(); i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->trace_events[i - 1].second, ctx->trace_events[i].second);
+    const char *w = strrchr(ctx->trace_events[i].first, '/');
+    std::string key = w ? w + 1 : ctx->trace_events[i].first;
+    bool found = false;
+    for (auto &a : agg)
+      if (a.first == key) { a.second.first++; a.second.second += ms; found = true; break; }
+    if (!found) agg.push_back({key, {1, (double)ms}});
+  }
+  fprintf(stderr, "[cg trace] %zu launches (time since the previous launch's end, incl. gaps)\n", ctx->trace_events.size());
+  for (auto &a : agg)
+    fprintf(stderr, "[cg trace] %-28s n=%5d total=%9.3f ms avg=%8.2f us\n", a.first.c_str(), a.second.first, a.second.second,
+            1e3 * a.second.second / a.second.first);
+  for (auto &t : ctx->trace_events) cudaEventDestroy(t.second);
+  ctx->trace_events.clear();
+}
 
 extern "C" int cg_ctx_profile(cg_ctx *ctx, int enable) {
   if (!ctx) return CG_EINVAL;

@@ -167,11 +167,48 @@ __device__ __forceinline__ bool point_hits(const SdfView &s, const float *G, int
 
 constexpr int FT = 256;
 
-__device__ bool any_point_hits(const SdfView &s, const float *inv, int mode, const float *__restrict__ pts, int P,
-                               volatile int *flag) {
+// Points whose trilinear lookup cannot be skipped are queued (grid coordinates) so that the eight-corner gather runs
+// with full warps: most scene points miss the gripper's grid box, and evaluating the survivors in place left ~46 % of
+// the lanes idle (ncu: 17.4 active threads per instruction).
+constexpr int QCAP = 4 * FT;
+struct HitQueue {
+  float x[QCAP], y[QCAP], z[QCAP];
+  int count[2];
+};
+
+__device__ bool any_point_hits(const SdfView &s, const float *G, int mode, const float *__restrict__ pts, int P,
+                               volatile int *flag, HitQueue &Q) {
   // four independent points per thread and iteration (12 loads in flight) -- the loop is latency-bound otherwise;
   // within one j the 256 threads read consecutive points (coalesced 12-byte rows)
-  bool hit = false;
+  if (!(mode == CG_SDF_TRILINEAR && s.border_nonneg)) {
+    bool hit = false;
+    for (int base = 0; base < P; base += 4 * FT) {
+      float x[4], y[4], z[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int p = base + j * FT + threadIdx.x;
+        ok[j] = p < P;
+        const size_t o = 3 * (size_t)(ok[j] ? p : 0);
+        x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) hit = hit || (ok[j] && point_hits(s, G, mode, x[j], y[j], z[j]));
+      if (hit) { *flag = 1; break; }
+      if (*flag) break;   // another thread already found a collision
+    }
+    return __syncthreads_or(hit) != 0;
+  }
+  // Trilinear with a non-negative border: the exact out-of-box shortcut of point_hits() decides most points; the rest
+  // go through the queue.  Same arithmetic per point as point_hits(), so the verdict is unchanged.
+  const float g0 = G[0], g1 = G[1], g2 = G[2], g3 = G[3], g4 = G[4], g5 = G[5], g6 = G[6], g7 = G[7], g8 = G[8];
+  const float t0 = G[9], t1 = G[10], t2 = G[11];
+  const float hx = (float)(s.nx - 1), hy = (float)(s.ny - 1), hz = (float)(s.nz - 1);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int cur = 0;
+  if (threadIdx.x == 0) { Q.count[0] = 0; Q.count[1] = 0; }
+  __syncthreads();
   for (int base = 0; base < P; base += 4 * FT) {
     float x[4], y[4], z[4];
     bool ok[4];
@@ -183,11 +220,31 @@ __device__ bool any_point_hits(const SdfView &s, const float *inv, int mode, con
       x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) hit = hit || (ok[j] && point_hits(s, inv, mode, x[j], y[j], z[j]));
-    if (hit) { *flag = 1; break; }
-    if (*flag) break;   // another thread already found a collision
+    for (int j = 0; j < 4; j++) {
+      const float gx = fmaf(g2, z[j], fmaf(g1, y[j], fmaf(g0, x[j], t0)));
+      const float gy = fmaf(g5, z[j], fmaf(g4, y[j], fmaf(g3, x[j], t1)));
+      const float gz = fmaf(g8, z[j], fmaf(g7, y[j], fmaf(g6, x[j], t2)));
+      const bool need = ok[j] && !(gx < 0.f || gy < 0.f || gz < 0.f || gx > hx || gy > hy || gz > hz);
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (m) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&Q.count[cur], __popc(m));
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (need) {
+          const int e = at + __popc(m & lt);
+          Q.x[e] = gx; Q.y[e] = gy; Q.z[e] = gz;
+        }
+      }
+    }
+    __syncthreads();
+    const int n = Q.count[cur];
+    if (threadIdx.x == 0) Q.count[cur ^ 1] = 0;      // next chunk's counter; nobody touches it before the barrier below
+    bool hit = false;
+    for (int e = threadIdx.x; e < n; e += FT) hit = hit || (sdf_trilinear(s, Q.x[e], Q.y[e], Q.z[e]) < 0.f);
+    if (__syncthreads_or(hit)) return true;
+    cur ^= 1;
   }
-  return __syncthreads_or(hit) != 0;
+  return false;
 }
 
 __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, const float *__restrict__ grasp_poses,
@@ -201,6 +258,7 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
   __shared__ float inv_s[12], go_s[12], ge_s[12];   // inverse gripper pose; folded camera->grid maps (open, enclosed)
   __shared__ int rej_dir;
   __shared__ int flag;
+  __shared__ HitQueue hq;
   const long q = blockIdx.x;
   const int i = (int)(q / S), j = (int)(q % S);
   if (threadIdx.x == 0) {
@@ -248,8 +306,8 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
       flag = 0;
     }
     __syncthreads();
-    bool coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, open_pts, P1, &flag);
-    if (!coll && P2 > 0) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts, P2, &flag);
+    bool coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, open_pts, P1, &flag, hq);
+    if (!coll && P2 > 0) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts, P2, &flag, hq);
     if (!coll) { winner = k; break; }
     __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
   }

@@ -24,6 +24,9 @@ struct cg_ctx {
   // optional event-pair timing of trunk launches (bench roofline)
   bool prof = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  // CG_TRACE=1 (diagnostics): an event after every launch; per-call-site durations are printed to stderr every 3000 launches
+  bool trace = false;
+  std::vector<std::pair<const char *, cudaEvent_t>> trace_events;
   // grow-only device workspace, carved per call
   void *ws = nullptr;
   size_t ws_bytes = 0;
@@ -52,9 +55,14 @@ struct cg_ctx {
     }                                                                             \
   } while (0)
 
+void cg_trace_mark(cg_ctx *ctx, const char *where);
+#define CG_STR2(x) #x
+#define CG_STR(x) CG_STR2(x)
+
 #define CG_LAUNCH_CHECK(ctx)                                                      \
   do {                                                                            \
     (ctx)->launches++;                                                            \
+    if ((ctx)->trace) cg_trace_mark((ctx), __FILE__ ":" CG_STR(__LINE__));        \
     cudaError_t _e = cudaGetLastError();                                          \
     if (_e != cudaSuccess) {                                                      \
       (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(_e);       \

@@ -14,13 +14,15 @@ class Sdf3D:
     point x in the SDF frame is (x - origin) / resolution (sdf.py:252-264).
     """
 
-    def __init__(self, sdf_data, origin, resolution, device=None):
+    def __init__(self, sdf_data, origin, resolution, device=None, ctx=None):
         self.data_ = np.ascontiguousarray(sdf_data, dtype=np.float32)
         assert self.data_.ndim == 3
         self.origin_ = np.asarray(origin, dtype=np.float32).reshape(3)
         self.resolution_ = float(np.float32(resolution))
         self.dims_ = np.array(self.data_.shape)
-        self.ctx = _lib.Context.get(device)
+        # ``ctx``: a library context of its own (= its own stream and workspace) lets the collision filter run
+        # concurrently with the networks of the per-device default context (bench.py does this)
+        self.ctx = ctx if ctx is not None else _lib.Context.get(device)
         h = C.c_void_p()
         org = (C.c_float * 3)(*[float(v) for v in self.origin_])
         nx, ny, nz = self.data_.shape
