@@ -306,8 +306,17 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
       flag = 0;
     }
     __syncthreads();
-    bool coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, open_pts, P1, &flag, hq);
-    if (!coll && P2 > 0) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts, P2, &flag, hq);
+    // The verdict is (open gripper hits the object's points) OR (swept gripper hits the background points), so the
+    // order of the scans is free (the reference does open first, common.cpp:268-278).  In clutter nearly every rejection
+    // comes from the background and shows up within the first points scanned, whereas the object's own points all lie
+    // inside the gripper's grid box (every one needs the eight-corner lookup) and never end the scan early.  So: the
+    // head of the background set, then the object set, then the rest of the background.  (`flag` is only ever set by a
+    // hit, so it is still clear whenever a later scan starts.)
+    const int head = min(P2, 4 * FT);
+    bool coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts, head, &flag, hq);
+    if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, open_pts, P1, &flag, hq);
+    if (!coll && P2 > head)
+      coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts + 3 * (size_t)head, P2 - head, &flag, hq);
     if (!coll) { winner = k; break; }
     __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
   }
