@@ -180,25 +180,29 @@ __global__ void __launch_bounds__(256) linear_wide_kernel(const float *__restric
 }
 
 
-// Few-row variant (M <= 8: the per-scene NUNOCS heads, B = 1): 64 output columns per CTA, K split over 16 thread
-// groups whose partial sums meet in shared memory -- latency-bound GEMV work that the tiled kernels serialise badly.
+// Few-row variant (M <= 8: the per-scene NUNOCS heads, B = 1): 16 output columns per CTA, K split over 64 thread
+// groups whose partial sums meet in shared memory -- latency-bound GEMV work that the tiled kernels serialise badly
+// (a 1024->512 layer is 32 CTAs of 16 dependent loop steps; with 64 columns x 16 slices it was 8 CTAs of 64 steps).
 constexpr int RM = 8;
+constexpr int RQ = 4;     // column quads per CTA
+constexpr int RS = 64;    // k-slices per CTA
+constexpr int RC = RQ * 4;
 
 __global__ void __launch_bounds__(256) linear_rows_kernel(const float *__restrict__ X, int M, int K,
                                                            const float *__restrict__ Wt,
                                                            const float *__restrict__ bias, int N, int relu,
                                                            int bias_row_div, int x_is_keys,
                                                            float *__restrict__ Y) {
-  __shared__ float red[16][RM][64 + 1];
+  __shared__ float red[RS][RM][RC + 1];
   const int tid = threadIdx.x;
-  const int nq = tid & 15, ks = tid >> 4;          // 16 column quads x 16 k-slices
-  const int n = blockIdx.x * 64 + nq * 4;
+  const int nq = tid % RQ, ks = tid / RQ;          // RQ column quads x RS k-slices
+  const int n = blockIdx.x * RC + nq * 4;
   float acc[RM][4];
 #pragma unroll
   for (int m = 0; m < RM; m++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[m][j] = 0.f;
-  const int kper = (K + 15) / 16;
+  const int kper = (K + RS - 1) / RS;
   const int k0 = ks * kper, k1 = min(K, k0 + kper);
   const bool vec = ((N & 3) == 0) && (n + 4 <= N);
 #pragma unroll 4
@@ -226,13 +230,13 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float *__restric
 #pragma unroll
     for (int j = 0; j < 4; j++) red[ks][m][nq * 4 + j] = acc[m][j];
   __syncthreads();
-  for (int o = tid; o < M * 64; o += 256) {
-    const int m = o >> 6, c = o & 63;
-    const int col = blockIdx.x * 64 + c;
+  for (int o = tid; o < M * RC; o += 256) {
+    const int m = o / RC, c = o % RC;
+    const int col = blockIdx.x * RC + c;
     if (col >= N) continue;
     float v = 0.f;
-#pragma unroll
-    for (int s2 = 0; s2 < 16; s2++) v += red[s2][m][c];
+#pragma unroll 8
+    for (int s2 = 0; s2 < RS; s2++) v += red[s2][m][c];
     if (bias) v += bias[(size_t)(bias_row_div > 0 ? (m / bias_row_div) : 0) * N + col];
     if (relu) v = fmaxf(v, 0.f);
     Y[(size_t)m * N + col] = v;
@@ -307,7 +311,7 @@ int cg_linear_launch(cg_ctx *ctx, const float *X, int M, int K, const float *Wt,
     if (rc != 0) return rc < 0 ? rc : CG_OK;
   }
   if (M <= RM) {
-    linear_rows_kernel<<<(N + 63) / 64, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
+    linear_rows_kernel<<<(N + RC - 1) / RC, 256, 0, ctx->stream>>>(X, M, K, Wt, bias, N, relu, bias_row_div, x_is_keys, Y);
     CG_LAUNCH_CHECK(ctx);
     return CG_OK;
   }
