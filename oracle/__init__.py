@@ -10,6 +10,10 @@ Pinning status (DESIGN.md section "Oracle"):
   * transforms_ref.py, aligning_ref.py : PINNED against the reference's own predicter.py / dataset_grasp.py /
     dataset_nunocs.py / augmentations.py / aligning.py / Utils.load_model executed in the authoring container with
     the absent third-party imports stubbed (tests/golden/make_golden_hostpath.py -> tests/golden/host_*.npz).
+  * sdf_ref.py                  : PINNED against the reference's meshpy Sdf3D lookups / SdfFile reader executed here
+    (tests/golden/make_golden_sdf.py -> sdf_lookup.npz).
+  * cone_ref.py                 : PINNED against poses recorded from the reference's PointConeGraspSampler.sample_grasps
+    (tests/golden/make_golden_cone.py -> cone_poses.npz).
   * filter_ref.c, occupancy_ref.c : pose logic / control flow PINNED against the reference's own my_cpp/common.cpp
     compiled by oracle/build_ref.py into oracle/_ref (bit-identical survivor sets / occupied samples,
     tests/golden/make_golden_mycpp.py -> tests/golden/mycpp_*.npz).  The FCL / octomap boundary cannot be built

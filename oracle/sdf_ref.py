@@ -2,7 +2,8 @@
 
 Used to show that the fp32 predicate of filter_ref.c / the CUDA kernel computes the reference's
 formula (sdf.py:292-343 trilinear, :345-359 nearest+clamp, :377-389 any-inside) up to fp32 round-off.
-meshpy itself cannot be imported here (autolab_core, open3d absent).
+PINNED: tests/test_sdf_golden.py compares these functions with outputs of the reference's own Sdf3D methods executed
+under import stubs (tests/golden/make_golden_sdf.py).
 """
 import numpy as np
 

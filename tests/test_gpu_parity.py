@@ -743,3 +743,17 @@ def test_cone_poses_feed_filter_on_device(cuda):
     assert np.array_equal(dst.cpu().numpy(), hst) and np.array_equal(doff.cpu().numpy(), hoff)
     assert np.array_equal(dout.cpu().numpy().view(np.uint32), hout.view(np.uint32))
     assert p32.shape[0] > 0 and p32.shape[0] % ((1 + 6 * 6) * 3) == 0 and (hst == 0).any() and (hst != 0).any()
+
+
+def test_sdf_lookups_vs_reference_run(cuda, golden_dir):
+    """Sdf3D lookups on the GPU vs values computed by the reference's own meshpy Sdf3D (tests/golden/make_golden_sdf.py)."""
+    from catgrasp_b200.sdf import Sdf3D
+    from catgrasp_b200.synthetic import make_gripper_proxy
+    g_ = np.load(os.path.join(golden_dir, "sdf_lookup.npz"))
+    g = make_gripper_proxy()["open"]
+    s = Sdf3D(g["sdf"], g["origin"], g["res"])
+    gc = g_["coords"]
+    tri = s._signed_distance(gc.T, fast=False).cpu().numpy()
+    near = s._signed_distance(gc.T, fast=True).cpu().numpy()
+    assert np.abs(tri - g_["trilinear"]).max() < 1e-6
+    np.testing.assert_allclose(near, g_["nearest_clamped"], rtol=0, atol=1e-7)
