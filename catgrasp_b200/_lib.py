@@ -69,6 +69,7 @@ SIGNATURES = {
     "cg_ransac9d_host": (_i, [_vp, _vp, _vp, _i, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "cg_cone_poses_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, C.c_double, _vp, _vp]),
     "cg_center_grasps_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i]),
+    "cg_grasp_affordance_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, C.c_double, _vp, _vp]),
     "cg_square_distance_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_index_points_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cg_fps_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),

@@ -218,6 +218,19 @@ int cg_cone_poses_dev(cg_ctx *ctx, const double *surface_pts, const double *R0, 
  * camera frame) in the grasp frame; poses are updated in place (poses32 may be NULL).                                */
 int cg_center_grasps_dev(cg_ctx *ctx, double *poses64, float *poses32, int P, const double *pts, int M);
 
+/* ---- Affordance transfer per grasp (device pointers, float64) --------------------------------
+ * Replaces: run_grasp_simulation.py:50-73 (compute_grasp_affordance_worker) + pybullet_env/env_grasp.py:243-283
+ *   (get_finger_contact_area) for G grasps at once.
+ *   cam_in_finger (G,16) = inv(finger_mesh_in_grasp) * inv(grasp_in_cam) per grasp (row-major 4x4, :52)
+ *   pts, nrm (P,3): the canonical cloud and normals in the camera frame; affordance (P): score of each point's nearest
+ *   canonical point (:62-63, gathered once per object on the host)
+ *   finger_boxes (F,4) = x min, x max, z min, z max of each finger mesh (:252); grip_dirs (F) = +1 / -1 for a finger closing
+ *   along +y / -y (:261-266); 1 <= F <= 4
+ *   out_p (G) = p(T|G), NaN where the reference drops the grasp; out_contacts (G,4) = contact-patch sizes per finger.   */
+int cg_grasp_affordance_dev(cg_ctx *ctx, const double *cam_in_finger, int G, const double *pts, const double *nrm,
+                            const double *affordance, int P, const double *finger_boxes, const int *grip_dirs, int F,
+                            double surface_tol, double *out_p, int *out_contacts);
+
 /* ---- PointNet++ primitives (device pointers) ---------------------------
  * Replace the free functions of pointnet2.py:14-149.  Indices are int32 on
  * the device (the Python mirror widens to int64 like the reference).        */

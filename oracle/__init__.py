@@ -12,6 +12,8 @@ Pinning status (DESIGN.md section "Oracle"):
     the absent third-party imports stubbed (tests/golden/make_golden_hostpath.py -> tests/golden/host_*.npz).
   * sdf_ref.py                  : PINNED against the reference's meshpy Sdf3D lookups / SdfFile reader executed here
     (tests/golden/make_golden_sdf.py -> sdf_lookup.npz).
+  * affordance_ref.py           : PINNED against the reference's compute_grasp_affordance_worker / get_finger_contact_area
+    (tests/golden/make_golden_affordance.py -> affordance.npz).
   * cone_ref.py                 : PINNED against poses recorded from the reference's PointConeGraspSampler.sample_grasps
     (tests/golden/make_golden_cone.py -> cone_poses.npz).
   * filter_ref.c, occupancy_ref.c : pose logic / control flow PINNED against the reference's own my_cpp/common.cpp

@@ -757,3 +757,26 @@ def test_sdf_lookups_vs_reference_run(cuda, golden_dir):
     near = s._signed_distance(gc.T, fast=True).cpu().numpy()
     assert np.abs(tri - g_["trilinear"]).max() < 1e-6
     np.testing.assert_allclose(near, g_["nearest_clamped"], rtol=0, atol=1e-7)
+
+
+# ------------------------------------------------------------------ affordance transfer (run_grasp_simulation.py:50-107), SURVEY 8f F4
+def test_grasp_affordance_vs_reference_run(cuda, golden_dir):
+    """compute_grasp_affordance on the GPU vs the reference's own worker (tests/golden/make_golden_affordance.py): same
+    dropped grasps, same contact-patch sizes, scores equal up to nearest-neighbour ties (<= 1e-3) and equal to the
+    tie-free oracle formulation to 1e-12."""
+    import test_affordance_golden as ta
+    from scipy.spatial import cKDTree
+    from catgrasp_b200.affordance import compute_grasp_affordance
+    from oracle import affordance_ref
+    g = np.load(os.path.join(golden_dir, "affordance.npz"))
+    full, affordance, down, down_n, boxes, fmig, poses = ta.affordance_case()
+    p, ncon = compute_grasp_affordance(poses, fmig, down, down_n, full, affordance, boxes, [[0, 1, 0], [0, -1, 0]], 0.005)
+    assert np.array_equal(np.isnan(p), np.isnan(g["p_T_given_G"]))
+    np.testing.assert_array_equal(ncon, g["n_contacts"])
+    ok = ~np.isnan(p)
+    assert np.abs(p[ok] - g["p_T_given_G"][ok]).max() < 1e-3
+    _, nn = cKDTree(full).query(down)
+    po, _ = affordance_ref.grasp_affordance_pointwise_nn(poses, fmig, down, down_n, affordance[nn], boxes, [1, -1], 0.005)
+    assert np.abs(p[ok] - po[ok]).max() < 1e-12
+    with pytest.raises(RuntimeError):
+        compute_grasp_affordance(poses[:1], fmig, down, down_n, full, affordance, boxes, [[1, 0, 0], [0, -1, 0]], 0.005)
