@@ -12,12 +12,18 @@ from catgrasp_b200 import grasp_sampler as gs  # noqa: E402
 from oracle import cone_ref  # noqa: E402
 
 CASES = [dict(n_pts=60, seed=4, n_sphere_dir=8, approach_step=0.005, center=False, max_num_samples=9),
-         dict(n_pts=40, seed=5, n_sphere_dir=5, approach_step=0.004, center=True, max_num_samples=np.inf)]
+         dict(n_pts=40, seed=5, n_sphere_dir=5, approach_step=0.004, center=True, max_num_samples=np.inf),
+         dict(pile=(2400, 6, 43, 3), n_sphere_dir=6, approach_step=0.004, center=False, max_num_samples=12)]
 HAND_DEPTH, INIT_BITE = 0.012, 0.002
 
 
 def case_inputs(c):
     from catgrasp_b200 import synthetic
+    if "pile" in c:
+        n, k, seed, obj = c["pile"]
+        scene = synthetic.make_pile(n, n_objects=k, seed=seed)
+        m = scene["object_id"] == obj
+        return scene["cloud_xyz"][m].copy(), scene["cloud_normal"][m].copy()
     rng = np.random.RandomState(c["seed"])
     pts, nrm = synthetic.sample_hex_nut(c["n_pts"], rng)
     R = synthetic.random_rotation(rng)
