@@ -221,3 +221,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""        # other ranks exit 0 without work
+
+
+def test_host_pose_composition_is_bit_identical_to_the_oracle():
+    """my_cpp.grasp_in_cam_unshifted (host fp32, feeds the IK stage) == oracle/filter_ref.c's pose arithmetic, which is
+    itself bit-identical to the reference's compiled filterGraspPose (tests/test_mycpp_golden.py)."""
+    from catgrasp_b200.my_cpp import grasp_in_cam_unshifted
+    from catgrasp_b200.synthetic import make_filter_case
+    from oracle import filter_ref
+    p1, p2, poses, sym, nocs_pose, c2n, g = make_filter_case(43, 64, 12, (1.0, 1.1, 0.9))
+    none = np.zeros((0, 3))
+    st, off, out = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], False, False, 0, g["open"], none,
+                                         g["enclosed"], none)
+    assert (st == 0).all()
+    u = grasp_in_cam_unshifted(poses, sym, nocs_pose, c2n)
+    assert np.array_equal(u.view(np.uint32), out.view(np.uint32))
