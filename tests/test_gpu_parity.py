@@ -701,7 +701,7 @@ def test_filterGraspPose_with_ik_equals_reference_build(cuda, golden_dir, k):
 
 
 # ------------------------------------------------------------------ cone pose enumeration (grasp_sampler.py:131-298), SURVEY 8f F3
-@pytest.mark.parametrize("k", range(2))
+@pytest.mark.parametrize("k", range(3))
 def test_cone_grasp_poses_vs_reference_run(cuda, golden_dir, k):
     """cone_grasp_poses == the poses the reference's own PointConeGraspSampler.sample_grasps handed to filterGraspPose
     (tests/golden/make_golden_cone.py), same numpy-RNG consumption; float64 to 1e-13, float32 copy = narrowed values."""
