@@ -9,7 +9,9 @@
 // arithmetic so that they agree bit for bit -- occupied set = cells floor(p / res) of the scan points (dense bit mask
 // over their bounding box); the ray is a 3-D DDA from the origin cell whose next-boundary parameters are recomputed
 // from the integer cell index at every step (no accumulation); a hit counts when |cell centre| <= |sample|.
-// Parity with octomap's own traversal is UNPINNED.
+// The reference's own function, compiled against a restatement of the octomap calls it makes (oracle/build_ref.py,
+// oracle/ref_shim/octomap/octomap.h), returns exactly the same samples (tests/test_mycpp_golden.py); parity with the
+// octomap library itself stays unpinned (not installed, version not pinned by the reference).
 #include "cg_common.cuh"
 
 namespace {
