@@ -14,6 +14,8 @@ Pinning status (DESIGN.md section "Oracle"):
     (tests/golden/make_golden_sdf.py -> sdf_lookup.npz).
   * affordance_ref.py           : PINNED against the reference's compute_grasp_affordance_worker / get_finger_contact_area
     (tests/golden/make_golden_affordance.py -> affordance.npz).
+  * fcl_semantic_ref.py         : NOT a pin -- a restatement of the FCL/octomap mesh-vs-voxel semantic used only to measure
+    the agreement rate of the SDF predicate with it (tests/test_fcl_semantic_agreement.py).
   * cone_ref.py                 : PINNED against poses recorded from the reference's PointConeGraspSampler.sample_grasps
     (tests/golden/make_golden_cone.py -> cone_poses.npz).
   * filter_ref.c, occupancy_ref.c : pose logic / control flow PINNED against the reference's own my_cpp/common.cpp
