@@ -15,7 +15,6 @@ import pickle
 import numpy as np
 import yaml
 
-from . import _lib
 from .net import PointNetCls, PointNetSeg
 from .weights import load_checkpoint
 

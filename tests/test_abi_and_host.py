@@ -1,7 +1,6 @@
 """CPU tests: the C ABI library loads and exports every symbol of include/*.h, host logic,
 weight folding, and that the product path fails loudly without a GPU / without the extension."""
 import copy
-import ctypes
 import os
 import re
 

@@ -3,7 +3,6 @@
 import os
 
 import numpy as np
-import torch
 
 from catgrasp_b200.synthetic import make_state_dict
 from oracle import pn2_ref
