@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--candidates", type=int, default=4096, help="candidates per GPU")
     ap.add_argument("--scene-pts", type=int, default=20000)
     ap.add_argument("--nunocs-pts", type=int, default=8192)
-    ap.add_argument("--engine", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 3-pass bf16, 2 tcgen05 2-pass fp16 (default: library default)")
+    ap.add_argument("--engine", type=int, default=None, help="0 fp32 SIMT, 1 tcgen05 3-pass bf16, 2 tcgen05 2-pass fp16, 3 persistent tcgen05 1-pass fp16 (default: library default = 3)")
     ap.add_argument("--cpu-sample", type=int, default=192, help="candidates in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", action="store_true",
@@ -332,7 +332,7 @@ def main():
 
     # ---------------- same workload on the 3-pass (near-fp32) tensor-core engine, for the record
     alt = None
-    if main_engine == 2:
+    if main_engine >= 2:
         ctx.set_engine(1)
         for _ in range(2):
             step_device()
@@ -439,7 +439,7 @@ def main():
         traffic = json.load(open(tpath)).get("mean_bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "trunk (fused shared-MLP 6-64-[64]-128-1024 + max)",
-                "engine": ["fp32-simt", "tcgen05-bf16x3", "tcgen05-f16x2"][main_engine],
+                "engine": ["fp32-simt", "tcgen05-bf16x3", "tcgen05-f16x2", "tcgen05-f16x1-persistent"][main_engine],
                 "launches_timed": int(trunk_n), "avg_launch_ms": per_launch_ms,
                 "share_of_step": trunk_ms / ms, "peak_source": f"{peaks['source']} bf16 dense, sustained",
                 "frac_of_burst_peak": achieved / peaks["bf16_tflops"]}
@@ -448,7 +448,8 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ["f32", "f32 (bf16 hi/lo x3 on tcgen05, f32 accumulate)",
-                      "f32 (f16 hi/lo x2 on tcgen05, f32 accumulate)"][main_engine],
+                      "f32 (f16 hi/lo x2 on tcgen05, f32 accumulate)",
+                      "f32 (128->1024 layer f16 x f16 single pass on tcgen05, f32 accumulate; other layers bf16 hi/lo x3)"][main_engine],
             "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "max_abs_dprob_vs_device_leg": agree},

@@ -46,6 +46,8 @@ SIGNATURES = {
     "cg_ctx_reset_launch_count": (None, [_vp]),
     "cg_ctx_set_engine": (_i, [_vp, _i]),
     "cg_ctx_get_engine": (_i, [_vp]),
+    "cg_ctx_fp16_overflow": (_i, [_vp, C.POINTER(_i)]),
+    "cg_tmem_layout_selftest": (_i, [_vp, _vp]),
     "cg_ctx_profile": (_i, [_vp, _i]),
     "cg_ctx_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "cg_net_create": (_i, [_vp, _i, _i, _vp, _sz, C.POINTER(_vp)]),
@@ -151,6 +153,12 @@ class Context:
 
     def get_engine(self):
         return int(self.lib.cg_ctx_get_engine(self.h))
+
+    def fp16_overflow(self):
+        """True if engine 2/3 had to clamp an activation to the fp16 range since the last call (clears the flag)."""
+        v = C.c_int()
+        self.check(self.lib.cg_ctx_fp16_overflow(self.h, C.byref(v)))
+        return bool(v.value)
 
     def profile(self, enable):
         self.check(self.lib.cg_ctx_profile(self.h, int(bool(enable))))

@@ -9,7 +9,11 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libcatgrasp_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "--expt-relaxed-constexpr"]
+
+
+if os.environ.get("CG_BUILD_EXPERIMENTS") == "1":   # developer builds only: CG_TRUNK_DEBUG / CG_TRUNK_EXP switches
+    NVCC_FLAGS.append("-DCG_EXPERIMENTS")
 
 
 def sources():
@@ -44,7 +48,8 @@ def build(force=False, verbose=False):
             print(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs)
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread",
+                           "-o", LIB] + objs)
     return LIB
 
 

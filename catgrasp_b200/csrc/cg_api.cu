@@ -27,7 +27,24 @@ extern "C" int cg_ctx_create(int device, cg_ctx **out) {
     return CG_ECUDA;
   }
   ctx->stream = ctx->own_stream;
+  if (cudaMalloc(&ctx->ovf_flag, 4) != cudaSuccess || cudaMemset(ctx->ovf_flag, 0, 4) != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return CG_ECUDA;
+  }
   *out = ctx;
+  return CG_OK;
+}
+
+// engine 3 clamps 128->1024 inputs to the fp16 range; *out = 1 if that happened since the last call (clears the flag)
+extern "C" int cg_ctx_fp16_overflow(cg_ctx *ctx, int *out) {
+  if (!ctx || !out) return CG_EINVAL;
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint32_t h = 0;
+  CG_CUDA(ctx, cudaMemcpyAsync(&h, ctx->ovf_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h) CG_CUDA(ctx, cudaMemsetAsync(ctx->ovf_flag, 0, 4, ctx->stream));
+  *out = (int)h;
   return CG_OK;
 }
 
@@ -35,6 +52,7 @@ extern "C" void cg_ctx_destroy(cg_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->ovf_flag) cudaFree(ctx->ovf_flag);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->io) cudaFree(ctx->io);
   if (ctx->hs) cudaFreeHost(ctx->hs);
@@ -67,7 +85,8 @@ extern "C" void cg_ctx_reset_launch_count(cg_ctx *ctx) { if (ctx) ctx->launches 
 
 extern "C" int cg_ctx_set_engine(cg_ctx *ctx, int engine) {
   if (!ctx) return CG_EINVAL;
-  CG_REQUIRE(ctx, engine >= 0 && engine <= 2, "engine must be 0 (fp32 SIMT), 1 (tcgen05 3-pass) or 2 (tcgen05 2-pass)");
+  CG_REQUIRE(ctx, engine >= 0 && engine <= 3,
+             "engine must be 0 (fp32 SIMT), 1 (tcgen05 3-pass), 2 (tcgen05 2-pass) or 3 (persistent tcgen05 1-pass)");
   ctx->engine = engine;
   return CG_OK;
 }

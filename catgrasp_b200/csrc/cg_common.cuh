@@ -13,13 +13,17 @@
 #error "libcatgrasp_b200 is written for sm_100a (B200) only"
 #endif
 
+constexpr int CG_MAX_DEVICES = 64;   // per-device one-time kernel attributes are tracked in arrays of this size
+
 struct cg_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
-  int engine = 2;  // 0 = fp32 SIMT, 1 = tcgen05 bf16 3-pass, 2 = tcgen05 fp16 2-pass (default)
+  // 0 = fp32 SIMT, 1 = tcgen05 bf16 3-pass, 2 = tcgen05 fp16 2-pass, 3 = persistent tcgen05, single fp16 pass (default)
+  int engine = 3;
+  uint32_t *ovf_flag = nullptr;   // device word: engine 3 saw a 128->1024 input above the fp16 range (clamped)
   int num_sms = 148;
   // optional event-pair timing of trunk launches (bench roofline)
   bool prof = false;

@@ -312,10 +312,10 @@ int cg_linear_tc_try(cg_ctx *ctx, const float *X, int M, int K, const float *Wt,
   if (ctx->engine < 1 || M < 64 || (K % 64) != 0) return 0;
   auto it = g_images.find(Wt);
   if (it == g_images.end()) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CG_MAX_DEVICES] = {};   // the attribute is per device
+  if (!attr_set[ctx->device]) {
     CG_CUDA(ctx, cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LSMEM));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   dim3 grid((N + 127) / 128, (M + 127) / 128);
   linear_tc_kernel<<<grid, LT, LSMEM, ctx->stream>>>(X, M, K, static_cast<const unsigned char *>(it->second), bias, N, relu,

@@ -110,7 +110,11 @@ int trunk_launch(cg_ctx *ctx, const cg_trunk_args &a) {
     CG_CUDA(ctx, cudaEventCreate(&e1));
     CG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
   }
-  const int rc = ctx->engine >= 1 ? cg_trunk_launch_tc(ctx, a) : cg_trunk_launch_simt(ctx, a);
+  int rc;
+  if (ctx->engine == 3 && a.tc_f16_ok) rc = cg_trunk_launch_p(ctx, a);   // persistent, single fp16 pass
+  else if (ctx->engine >= 1) rc = cg_trunk_launch_tc(ctx, a);            // 3-pass bf16 / 2-pass fp16 (also the
+                                                                          // fallback when W3 exceeds the fp16 range)
+  else rc = cg_trunk_launch_simt(ctx, a);
   if (ctx->prof) {
     CG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     ctx->prof_events.emplace_back(e0, e1);
@@ -147,7 +151,7 @@ int encoder_forward(cg_net *net, const cg_input_src &in, int B, int N, EncoderWs
   const cg_layer *L = net->L;
   int rc;
   cg_trunk_args a;
-  a.in = in; a.B = B; a.N = N; a.dbg = nullptr; a.exp_flags = 0;
+  a.in = in; a.B = B; a.N = N; a.dbg = nullptr; a.exp_flags = 0; a.ovf_flag = ctx->ovf_flag;
   // --- trunk A: STN3d convs + max (pointnet2.py:170-175)
   CG_CUDA(ctx, cudaMemsetAsync(w.gmax, 0, (size_t)B * 1024 * 4, ctx->stream));
   a.T3 = nullptr; a.l0 = L[L_S3_C1]; a.stage1_mode = 0; a.l1 = cg_layer{nullptr, nullptr, 0, 0}; a.T64 = nullptr;

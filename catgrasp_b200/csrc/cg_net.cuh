@@ -59,12 +59,14 @@ struct cg_trunk_args {
   uint32_t *gmax_keys;  // (B,1024) order-preserving keys, zero-initialised by the launcher
   float *pf_out;        // (B,N,64) stage-1 output (PointNetSeg point feature) or nullptr
   unsigned long long *dbg;  // optional per-CTA cycle counters (CG_TRUNK_DEBUG=1), else nullptr
+  uint32_t *ovf_flag;       // engine 3: set to 1 when an activation had to be clamped to the fp16 range (or nullptr)
   int exp_flags;            // timing experiments only (CG_TRUNK_EXP bitmask, results become wrong): 1 = no W3 copies,
                             // 2 = max warps skip the TMEM reads, 4 = front warps skip their math
 };
 
 int cg_trunk_launch_simt(cg_ctx *ctx, const cg_trunk_args &a);
 int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a);
+int cg_trunk_launch_p(cg_ctx *ctx, const cg_trunk_args &a);   // persistent single-pass kernel (engine 3)
 size_t cg_tc_image_bytes();
 // Wt3 [128][1024], Wt2 [64][128], Wt1 [64][64] or nullptr (folded fp32, k-major rows, host)
 int cg_tc_prepare(cg_ctx *ctx, const float *Wt3, const float *Wt2, const float *Wt1, void *dst_dev, int *f16_ok);

@@ -174,11 +174,11 @@ extern "C" int cg_fps_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoin
   const size_t full = (size_t)N * 16, dist_only = (size_t)N * 4;
   const size_t cap = 220 * 1024;
   CG_REQUIRE(ctx, dist_only <= cap, "fps: N too large for the shared-memory distance array (max 56320)");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CG_MAX_DEVICES] = {};   // the attribute is per device
+  if (!attr_set[ctx->device]) {
     CG_CUDA(ctx, cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     CG_CUDA(ctx, cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   if (full <= cap)
     fps_kernel<true><<<B, FPS_T, full, ctx->stream>>>(xyz, N, npoint, start_idx, out_idx);

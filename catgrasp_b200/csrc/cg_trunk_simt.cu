@@ -231,11 +231,11 @@ __global__ void __launch_bounds__(NT, 1) trunk_simt_kernel(const cg_trunk_args a
 int cg_trunk_launch_simt(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_REQUIRE(ctx, a.B > 0 && a.N > 0, "trunk: B,N must be positive");
   CG_REQUIRE(ctx, a.B <= 65535, "trunk: B > 65535 must be chunked by the caller");
-  static bool attr_set = false;
+  static bool attr_set[CG_MAX_DEVICES] = {};   // the attribute is per device
   const size_t smem = sizeof(SmemLayout);
-  if (!attr_set) {
+  if (!attr_set[ctx->device]) {
     CG_CUDA(ctx, cudaFuncSetAttribute(trunk_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   const int ntiles = (a.N + TP - 1) / TP;
   // enough CTAs to fill the machine ~4x over; one CTA per candidate when B is large

@@ -801,22 +801,29 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_REQUIRE(ctx, a.B > 0 && a.N > 0, "trunk: B,N must be positive");
   CG_REQUIRE(ctx, a.B <= 65535, "trunk: B > 65535 must be chunked by the caller");
   CG_REQUIRE(ctx, a.tc_img != nullptr, "trunk: tensor-core weight image missing");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[CG_MAX_DEVICES] = {};   // the attribute is per device
+  if (!attr_set[ctx->device]) {
     CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     CG_CUDA(ctx, cudaFuncSetAttribute(trunk_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_set = true;
+    attr_set[ctx->device] = true;
   }
   const int ntiles = (a.N + TP - 1) / TP;
   int splits = 1;
   while ((long)a.B * splits < 4L * ctx->num_sms && splits < ntiles) splits *= 2;
   const int tiles_per_cta = (ntiles + splits - 1) / splits;
   dim3 grid((ntiles + tiles_per_cta - 1) / tiles_per_cta, a.B);
-  const bool two_pass = ctx->engine == 2 && a.tc_f16_ok;
+  const bool two_pass = ctx->engine >= 2 && a.tc_f16_ok;
+#ifdef CG_EXPERIMENTS   // timing experiments (results become wrong): never read from the environment in a release build
   static const bool ts_mode = getenv("CG_TRUNK_SS") == nullptr;   // A operand of L3 from TMEM unless CG_TRUNK_SS is set
   static const int exp_flags = getenv("CG_TRUNK_EXP") ? atoi(getenv("CG_TRUNK_EXP")) : 0;
+  static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
+#else
+  constexpr bool ts_mode = true;
+  constexpr int exp_flags = 0;
+  constexpr bool debug = false;
+#endif
   auto launch = [&](const cg_trunk_args &a0) {
     cg_trunk_args aa = a0;
     aa.exp_flags = exp_flags;
@@ -828,7 +835,6 @@ int cg_trunk_launch_tc(cg_ctx *ctx, const cg_trunk_args &a) {
       else trunk_tc_kernel<3, false><<<grid, NTC, SMEM_BYTES, ctx->stream>>>(aa, tiles_per_cta);
     }
   };
-  static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
   if (debug) {
     cg_trunk_args ad = a;
     const size_t n = (size_t)grid.x * grid.y;

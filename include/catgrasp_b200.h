@@ -56,10 +56,20 @@ void        cg_ctx_reset_launch_count(cg_ctx *ctx);
  *   0 = fp32 SIMT (exact-order reference engine)
  *   1 = tcgen05, bf16 hi/lo x hi/lo, 3 passes (near-fp32: |dprob| ~ 1e-7)
  *   2 = tcgen05, 128->1024 layer with fp16 hi/lo activations x one fp16 weight
- *       term, 2 passes (|dprob| ~ 2e-6 vs the 1e-4 tolerance)               [default]
- *       (falls back to 1 for a net whose folded weights exceed the fp16 range) */
+ *       term, 2 passes (|dprob| ~ 2e-6 vs the 1e-4 tolerance)
+ *   3 = persistent tcgen05 kernel (one CTA per SM looping over candidates), the
+ *       128->1024 layer as ONE fp16 x fp16 pass (|dprob| ~ 4e-6)            [default]
+ *   (2 and 3 fall back to 1 for a net whose folded weights exceed the fp16 range) */
 int         cg_ctx_set_engine(cg_ctx *ctx, int engine);
 int         cg_ctx_get_engine(cg_ctx *ctx);
+/* Engines 2/3 clamp the 128->1024 layer's inputs to the fp16 range (65504).
+ * *out = 1 if a clamp happened on this context since the previous call (the
+ * flag is cleared); the caller should then re-run on engine 1.  Synchronises
+ * the context's stream.                                                      */
+int         cg_ctx_fp16_overflow(cg_ctx *ctx, int *out);
+/* Diagnostic: exercises the TMEM fragment layout the engine-3 max epilogue
+ * relies on; out_host receives 768 floats (see tests/test_gpu_parity.py).    */
+int         cg_tmem_layout_selftest(cg_ctx *ctx, float *out_host);
 /* Optional in-stream timing of the dominant kernel (the fused shared-MLP+max
  * "trunk"): when enabled every trunk launch is bracketed by a CUDA event pair
  * on the launching stream; cg_ctx_profile_read() synchronises those events and
