@@ -55,6 +55,13 @@ SIGNATURES = {
     "cg_net_blob_floats": (_sz, [_i, _i]),
     "cg_graspq_forward_host": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "cg_graspq_forward_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "cg_host_legacy_choice": (_i, [_vp, C.POINTER(C.c_int32), C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32]),
+    "cg_draw_ids_dev": (_i, [_vp, _i, _i, _i, C.c_uint64, C.c_int64, _vp]),
+    "cg_mlp_create": (_i, [_vp, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "cg_mlp_destroy": (None, [_vp]),
+    "cg_shared_mlp_dev": (_i, [_vp, _vp, C.c_int64, _vp]),
+    "cg_group_mlp_max_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+    "cg_three_interp_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "cg_cls_forward_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "cg_seg_forward_dev": (_i, [_vp, _vp, _i, _i, _vp]),
     "cg_nunocs_forward_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
@@ -144,6 +151,9 @@ class Context:
         import torch
         s = torch.cuda.current_stream(self.device).cuda_stream
         self.check(self.lib.cg_ctx_set_stream(self.h, C.c_void_p(s)))
+
+    def use_own_stream(self):
+        self.check(self.lib.cg_ctx_use_own_stream(self.h))
 
     def synchronize(self):
         self.check(self.lib.cg_ctx_synchronize(self.h))

@@ -31,6 +31,7 @@ def estimate9DTransform(source, target, PassThreshold, max_iter=1000, use_kdtree
     ratio = np.empty(max_iter, np.float64)
     T = np.empty((max_iter, 4, 4), np.float64)
     valid = np.empty(max_iter, np.uint8)
+    ctx.use_own_stream()   # blocking host call
     ctx.check(ctx.lib.cg_ransac9d_host(ctx.h, _lib.ptr(source), _lib.ptr(target), N, _lib.ptr(ids), max_iter,
                                        C.c_double(float(PassThreshold)), _lib.ptr(mins), _lib.ptr(maxs), _lib.ptr(mdim),
                                        _lib.ptr(ratio), _lib.ptr(T), _lib.ptr(valid)))

@@ -79,6 +79,12 @@ struct MiscP {
   uint32_t tmem_base;
 };
 
+#ifdef CG_EXPERIMENTS
+#define CG_EXP(a, bit) (((a).exp_flags & (bit)) != 0)
+#else
+#define CG_EXP(a, bit) false
+#endif
+
 constexpr size_t SMEM_BYTES_P = MISC_OFF + sizeof(MiscP) + 1024;   // + slack for manual 1024-byte alignment
 static_assert(SMEM_BYTES_P <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
@@ -190,15 +196,19 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const int total = T * NCHUNK;
     int slot = 0;
     uint32_t ph = 1u;   // a fresh barrier passes a wait on parity 1: the first round does not block
-    int chunk = (int)(((long long)g0 * NCHUNK) % NCHUNK);   // = 0: every tile starts with chunk 0
+    int chunk = 0;   // every tile starts with chunk 0
     for (int gp = 0; gp < total; gp++) {
       mbar_wait(smem_u32(&S.free_bar[slot]), ph);
       if (elect_one()) {
         const uint32_t fb = smem_u32(&S.full_bar[slot]);
-        mbar_expect_tx(fb, 2 * PIECE);
-        const unsigned char *src = w3src + (size_t)chunk * 2 * PIECE;
-        bulk_g2s(ring_s + (uint32_t)slot * 2 * PIECE, src, PIECE, fb);
-        bulk_g2s(ring_s + (uint32_t)slot * 2 * PIECE + PIECE, src + PIECE, PIECE, fb);
+        if (CG_EXP(a, 1) && gp >= NPAIR) {
+          mbar_arrive(fb);   // timing experiment: no W3 traffic after the first round
+        } else {
+          mbar_expect_tx(fb, 2 * PIECE);
+          const unsigned char *src = w3src + (size_t)chunk * 2 * PIECE;
+          bulk_g2s(ring_s + (uint32_t)slot * 2 * PIECE, src, PIECE, fb);
+          bulk_g2s(ring_s + (uint32_t)slot * 2 * PIECE + PIECE, src + PIECE, PIECE, fb);
+        }
       }
       __syncwarp();
       chunk = (chunk + 1) & (NCHUNK - 1);
@@ -251,7 +261,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     int rslot = 0;
     uint32_t rph = 0u;
     int b_prev = -1;
-    long long t_all = clock64(), t_x3 = 0, t_ring = 0, t_x12 = 0, tw;
+    long long t_all = clock64(), t_x3 = 0, t_ring = 0, t_accf = 0, t_x12 = 0, tw;
     // front layers (L1, L2) of local tile `itn`
     auto issue_l1 = [&](int itn) {
       int b, tile;
@@ -266,7 +276,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       ph_x1 ^= 1u;
       tc_fence_after();
       if (elect_one()) {
-        issue_k64(tmem_base + xb_col(itn), xa_s, PIECE, w1_s + (uint32_t)slot * PIECE, 8192u, umma_idesc(128, 64));
+        if (!CG_EXP(a, 8))
+          issue_k64(tmem_base + xb_col(itn), xa_s, PIECE, w1_s + (uint32_t)slot * PIECE, 8192u, umma_idesc(128, 64));
         umma_commit(l1b);
         if (percand_w1 && last_of_cand) umma_commit(smem_u32(&S.w1_free[slot]));
       }
@@ -277,7 +288,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       ph_x2 ^= 1u;
       tc_fence_after();
       if (elect_one()) {
-        issue_k64(tmem_base + xb_col(itn), xa_s, PIECE, w2_s, PIECE, umma_idesc(128, 128));
+        if (!CG_EXP(a, 8)) issue_k64(tmem_base + xb_col(itn), xa_s, PIECE, w2_s, PIECE, umma_idesc(128, 128));
         umma_commit(l2b);
       }
       __syncwarp();
@@ -294,18 +305,24 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       for (int c = 0; c < NCHUNK; c++) {
         const int buf = c & 1;
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
-        tw = clock64();
-        if (use >= 1u)
-          mbar_wait2(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u, smem_u32(&S.full_bar[rslot]), rph);
-        else
+        if (a.dbg) {   // instrumented run: time the two waits separately
+          tw = clock64();
+          if (use >= 1u) mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
+          t_accf += clock64() - tw;
+          tw = clock64();
           mbar_wait(smem_u32(&S.full_bar[rslot]), rph);
-        t_ring += clock64() - tw;
+          t_ring += clock64() - tw;
+        } else if (use >= 1u) {
+          mbar_wait2(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u, smem_u32(&S.full_bar[rslot]), rph);
+        } else {
+          mbar_wait(smem_u32(&S.full_bar[rslot]), rph);
+        }
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)buf * 128u;
         if (elect_one()) {
           const uint32_t w_s = ring_s + (uint32_t)rslot * 2 * PIECE;
 #pragma unroll
-          for (int i = 0; i < 2; i++) {
+          for (int i = 0; i < (CG_EXP(a, 16) ? 0 : 2); i++) {
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
               // D3[pt][ch] += X3[pt][k] (TMEM, 8 packed columns per K-step) . W3[ch][k] (smem)
@@ -332,8 +349,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       }
     }
     if (a.dbg && lane == 0) {
-      unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 8;
-      dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_ring; dd[3] = 0; dd[4] = t_x12; dd[5] = T;
+      unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
+      dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_ring; dd[3] = t_accf; dd[4] = t_x12; dd[5] = T;
     }
   } else if (warp >= NFRONT) {
     // ======================= max warps: L3 epilogue =======================
@@ -345,6 +362,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const int mt = tid - NFT;   // 0..127
     int b_cur, tile_cur;
     locate(0, b_cur, tile_cur);
+    long long m_all = clock64(), m_wait = 0, mw;
     for (int it = 0; it < T; it++) {
       int b_next = -1, tile_next = 0;
       if (it + 1 < T) locate(it + 1, b_next, tile_next);
@@ -353,11 +371,19 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       for (int c = 0; c < NCHUNK; c++) {
         const int buf = c & 1;
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);
+        mw = clock64();
         mbar_wait(smem_u32(&S.acc_bar[buf]), use & 1u);
+        m_wait += clock64() - mw;
         tc_fence_after();
         const uint32_t col0 = tmem_base + (uint32_t)buf * 128u;
         uint32_t ra[32], rb[32];
         float r0[2], r1[2];
+        if (CG_EXP(a, 2)) {   // timing experiment: no TMEM reads, no reduction
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&S.accfree_bar[buf]));
+          continue;
+        }
         tmem_ld_16x256b_x8(col0 + lane_lo, ra);
         tmem_ld_16x256b_x8(col0 + lane_hi, rb);
         tmem_ld_wait();
@@ -391,12 +417,17 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       b_cur = b_next;
       tile_cur = tile_next;
     }
+    if (a.dbg && tid == NFT) {
+      unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
+      dd[6] = clock64() - m_all; dd[7] = m_wait;
+    }
   } else {
     // ======================= front warps: thread = (point, channel half) =======================
     const int p = tid & 127, half = tid >> 7;
     const int q = warp & 3;                         // TMEM lane quadrant of this warp
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     unsigned ovf = 0u;
+    long long f_all = clock64(), f_l2 = 0, f_l1 = 0, fw;
     // raw input row of this thread's point for the tile being prepared (prefetched one tile ahead so that the
     // dependent global loads ids -> cloud row are off the critical path between two tiles)
     double rx[6];
@@ -479,8 +510,16 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     };
     // L1 epilogue of local tile `it`: D1 -> (bias, ReLU | nothing) -> XA as the L2 input
     auto l1_epilogue = [&](int it) {
+      const long long fw1 = clock64();
       mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
+      f_l1 += clock64() - fw1;
       tc_fence_after();
+      if (CG_EXP(a, 4)) {   // timing experiment: front warps skip their math
+        tc_fence_before();
+        bar_front();
+        if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
+        return;
+      }
       float v[32];
       tmem_ld32(tmem_base + lane_sel + xb_col(it) + (uint32_t)half * 32u, v);
       if (a.stage1_mode == 1) {
@@ -517,8 +556,31 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     for (int it = 0; it < T; it++) {
       const bool has_next = it + 1 < T;
       // A. D2(it) complete; its UMMAs no longer read XA
+      fw = clock64();
       mbar_wait(smem_u32(&S.l2_bar), (uint32_t)it & 1u);
+      f_l2 += clock64() - fw;
       tc_fence_after();
+      if (CG_EXP(a, 4)) {
+        tc_fence_before();
+        bar_front();
+        if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
+        if (has_next) {
+          int b, tile, bn, tn;
+          locate(it + 1, b, tile);
+          const int lc = b - b_first, slot = lc & 1;
+          if (b != b_l0) mbar_wait(smem_u32(&S.cc_full[slot]), ((uint32_t)lc >> 1) & 1u);
+          b_l0 = b;
+          const bool last_of_cand = (it + 1 == T - 1) || (locate(it + 2, bn, tn), bn != b);
+          fence_proxy_async();
+          bar_front();
+          if (tid == 0) {
+            mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
+            if (last_of_cand) mbar_arrive(smem_u32(&S.cc_free[slot]));
+          }
+          if (has_l1) l1_epilogue(it + 1);
+        }
+        continue;
+      }
       // C. L2 epilogue: D2 -> bias, ReLU -> fp16 pairs; written back IN PLACE as the TMEM A operand of L3
       uint32_t ph[32];
 #pragma unroll
@@ -553,6 +615,10 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       if (has_next && has_l1) l1_epilogue(it + 1);
     }
     if (ovf && a.ovf_flag) atomicOr(a.ovf_flag, 1u);
+    if (a.dbg && tid == 0) {
+      unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
+      dd[8] = clock64() - f_all; dd[9] = f_l2; dd[10] = f_l1;
+    }
   }
 
   tc_fence_before();
@@ -611,12 +677,14 @@ int cg_trunk_launch_p(cg_ctx *ctx, const cg_trunk_args &a) {
   const int total = a.B * ntiles;
   const int grid = total < ctx->num_sms ? total : ctx->num_sms;
   cg_trunk_args aa = a;
-#ifdef CG_EXPERIMENTS
+#ifdef CG_EXPERIMENTS   // developer builds only (never read from the environment in a release build)
   static const bool debug = getenv("CG_TRUNK_DEBUG") != nullptr;
+  static const int exp_flags = getenv("CG_TRUNK_EXP") ? atoi(getenv("CG_TRUNK_EXP")) : 0;
+  aa.exp_flags = exp_flags;
   unsigned long long *d_dbg = nullptr;
   if (debug) {
-    CG_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)grid * 64));
-    CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)grid * 64, ctx->stream));
+    CG_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)grid * 128));
+    CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)grid * 128, ctx->stream));
     aa.dbg = d_dbg;
   }
 #endif
@@ -624,16 +692,18 @@ int cg_trunk_launch_p(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_LAUNCH_CHECK(ctx);
 #ifdef CG_EXPERIMENTS
   if (debug) {
-    std::vector<unsigned long long> h((size_t)grid * 8);
-    CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, (size_t)grid * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> h((size_t)grid * 16);
+    CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, (size_t)grid * 128, cudaMemcpyDeviceToHost, ctx->stream));
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_dbg);
-    double s[6] = {0, 0, 0, 0, 0, 0};
+    double s[16] = {0};
     for (int i = 0; i < grid; i++)
-      for (int k = 0; k < 6; k++) s[k] += (double)h[(size_t)i * 8 + k];
+      for (int k = 0; k < 16; k++) s[k] += (double)h[(size_t)i * 16 + k];
     const double tiles = s[5] > 0 ? s[5] : 1;
-    fprintf(stderr, "[trunk_p dbg] CTAs=%d tiles=%.0f  MMA thread per tile: total %.0f  x3-wait %.0f  x1/x2-wait %.0f  ring+accfree-wait %.0f cycles\n",
-            grid, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles);
+    fprintf(stderr, "[trunk_p dbg] exp=%d CTAs=%d tiles=%.0f per tile: MMA total %.0f x3-wait %.0f x1/x2-wait %.0f ring-wait %.0f accfree-wait %.0f | "
+            "max total %.0f acc-wait %.0f | front total %.0f l2-wait %.0f l1-wait %.0f cycles\n",
+            exp_flags, grid, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles, s[3] / tiles, s[6] / tiles, s[7] / tiles,
+            s[8] / tiles, s[9] / tiles, s[10] / tiles);
   }
 #endif
   return CG_OK;

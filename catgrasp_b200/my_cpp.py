@@ -95,6 +95,7 @@ def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_noc
     status = np.empty((Q,), np.uint8)
     offset = np.empty((Q,), np.int8)
     poses = np.empty((Q, 4, 4), np.float32)
+    ctx.use_own_stream()   # blocking host call
     ctx.check(ctx.lib.cg_filter_grasp_pose_host(
         ctx.h, C.byref(prm), _lib.ptr(gp), G, _lib.ptr(st), S, sdf_open.h, _lib.ptr(p1), p1.shape[0],
         sdf_enclosed.h if sdf_enclosed is not None else None, _lib.ptr(p2), p2.shape[0],
@@ -186,6 +187,7 @@ def makeOccupancyGridFromCloudScan(pts, K, resolution):
     if nx * ny * nz == 0:
         return np.zeros((0, 3), np.float32)
     flags = np.empty(nx * ny * nz, np.uint8)
+    ctx.use_own_stream()   # blocking host call
     ctx.check(ctx.lib.cg_occupancy_from_scan_host(ctx.h, _lib.ptr(p), p.shape[0], C.c_float(res), _lib.ptr(flags)))
     idx = np.nonzero(flags)[0]
     xi, yi, zi = idx // (ny * nz), (idx // nz) % ny, idx % nz

@@ -55,14 +55,26 @@ class PointNetCls(_Net):
 
     __call__ = forward
 
-    def graspq_dev(self, cloud_xyz, cloud_nrm, poses, ids, mean=None, std=None):
+    def draw_ids_dev(self, M, n_pts, count, seed, first_candidate=0):
+        """Counter-based subset draw on the device (cg_draw_ids_dev): (count, n_pts) int32 cuda tensor."""
+        self.ctx.use_torch_stream()
+        ids = torch.empty((count, n_pts), dtype=torch.int32, device=self.device)
+        self.ctx.check(self.ctx.lib.cg_draw_ids_dev(self.ctx.h, int(M), int(n_pts), int(count), C.c_uint64(int(seed)),
+                                                    C.c_int64(int(first_candidate)), _lib.ptr(ids)))
+        return ids
+
+    def graspq_dev(self, cloud_xyz, cloud_nrm, poses, ids, mean=None, std=None, out=None):
         """Fused transform + forward + softmax on device tensors; returns (probs (B,n_out) f32, label (B,) i32)."""
         M = cloud_xyz.shape[0]
         B = poses.shape[0]
         N = ids.shape[1]
         self.ctx.use_torch_stream()
-        probs = torch.empty((B, self.n_out), dtype=torch.float32, device=self.device)
-        label = torch.empty((B,), dtype=torch.int32, device=self.device)
+        if out is not None:
+            probs, label = out
+            assert probs.is_contiguous() and label.is_contiguous() and poses.is_contiguous() and ids.is_contiguous()
+        else:
+            probs = torch.empty((B, self.n_out), dtype=torch.float32, device=self.device)
+            label = torch.empty((B,), dtype=torch.int32, device=self.device)
         self.ctx.check(self.ctx.lib.cg_graspq_forward_dev(
             self.h, _lib.ptr(cloud_xyz), _lib.ptr(cloud_nrm), M, _lib.ptr(poses), B, _lib.ptr(ids), N,
             _lib.ptr(mean), _lib.ptr(std), _lib.ptr(probs), _lib.ptr(label)))
@@ -77,6 +89,7 @@ class PointNetCls(_Net):
             out_probs = np.empty((B, self.n_out), dtype=np.float32)
         if out_label is None:
             out_label = np.empty((B,), dtype=np.int32)
+        self.ctx.use_own_stream()      # blocking host call: never on a (possibly freed) torch stream of an earlier _dev call
         self.ctx.check(self.ctx.lib.cg_graspq_forward_host(
             self.h, _lib.ptr(cloud_xyz), _lib.ptr(cloud_nrm), M, _lib.ptr(poses), B, _lib.ptr(ids), N,
             _lib.ptr(mean), _lib.ptr(std), _lib.ptr(out_probs), _lib.ptr(out_label)))
@@ -105,6 +118,7 @@ class PointNetSeg(_Net):
         coords = np.empty((N, 3), np.float32)
         conf = np.empty((N,), np.float32)
         b = np.empty((N, 3), np.int32)
+        self.ctx.use_own_stream()
         self.ctx.check(self.ctx.lib.cg_nunocs_forward_host(self.h, _lib.ptr(x), N, int(bins), _lib.ptr(coords),
                                                            _lib.ptr(conf), _lib.ptr(b)))
         return coords, conf, b

@@ -108,3 +108,105 @@ def sample_and_group_all(xyz, points):
     else:
         new_points = grouped_xyz
     return new_xyz, new_points
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Set-abstraction / feature-propagation modules (the upstream family the reference cites at pointnet2.py:274,304),
+# built on the primitives above.  Weights follow the upstream state_dict layout:
+#   mlp_convs.{i}.weight (C_out, C_in, 1[, 1]) / .bias,  mlp_bns.{i}.{weight,bias,running_mean,running_var}
+class _SharedMLP:
+    def __init__(self, state_dict, nlayers, device=None):
+        import ctypes as C
+        from .weights import _fold
+        self.ctx = _lib.Context.get(device)
+        sd = {k.replace("module.", ""): v for k, v in state_dict.items()}
+        Wts, bs, dims = [], [], []
+        for i in range(nlayers):
+            w = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in sd.items()
+                 if k.startswith(f"mlp_convs.{i}.") or k.startswith(f"mlp_bns.{i}.")}
+            w[f"mlp_convs.{i}.weight"] = w[f"mlp_convs.{i}.weight"].reshape(w[f"mlp_convs.{i}.weight"].shape[0], -1, 1)
+            Wt, b = _fold(w, f"mlp_convs.{i}", f"mlp_bns.{i}")
+            Wts.append(np.ascontiguousarray(Wt, dtype=np.float32))
+            bs.append(np.ascontiguousarray(b, dtype=np.float32))
+            dims.append(Wt.shape[0])
+        dims.append(Wts[-1].shape[1])
+        self.dims = dims
+        cdims = (C.c_int * len(dims))(*dims)
+        cw = (C.c_void_p * nlayers)(*[w.ctypes.data for w in Wts])
+        cb = (C.c_void_p * nlayers)(*[b.ctypes.data for b in bs])
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.cg_mlp_create(self.ctx.h, nlayers, cdims, cw, cb, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.ctx.lib.cg_mlp_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class PointNetSetAbstraction:
+    """forward(xyz (B,3,N), points (B,D,N) | None) -> (new_xyz (B,3,S), new_points (B,C_out,S)).
+
+    sample_and_group (pointnet2.py:101-129) / sample_and_group_all (:132-149), then [conv1x1 + BN + ReLU] x L over
+    every (group, member) row and a max over the group's nsample members."""
+
+    def __init__(self, npoint, radius, nsample, in_channel, mlp, group_all, state_dict, device=None):
+        self.npoint, self.radius, self.nsample, self.group_all = npoint, radius, nsample, group_all
+        self.mlp = _SharedMLP(state_dict, len(mlp), device=device)
+        assert self.mlp.dims[0] == in_channel and list(self.mlp.dims[1:]) == list(mlp), (self.mlp.dims, in_channel, mlp)
+
+    def forward(self, xyz, points, start_idx=None):
+        xyz = _f32(xyz.permute(0, 2, 1))
+        pts = None if points is None else _f32(points.permute(0, 2, 1))
+        if self.group_all:
+            new_xyz, new_points = sample_and_group_all(xyz, pts)
+        else:
+            new_xyz, new_points = sample_and_group(self.npoint, self.radius, self.nsample, xyz, pts, start_idx=start_idx)
+        new_points = _f32(new_points)
+        B, S, K, Cin = new_points.shape
+        ctx = _ctx(new_points)
+        out = torch.empty((B, S, self.mlp.dims[-1]), dtype=torch.float32, device=xyz.device)
+        ctx.check(ctx.lib.cg_group_mlp_max_dev(self.mlp.h, _lib.ptr(new_points), B * S, K, _lib.ptr(out)))
+        return new_xyz.permute(0, 2, 1), out.permute(0, 2, 1)
+
+    __call__ = forward
+
+
+class PointNetFeaturePropagation:
+    """forward(xyz1 (B,3,N), xyz2 (B,3,S), points1 (B,D1,N) | None, points2 (B,D2,S)) -> (B,C_out,N).
+
+    Inverse-distance interpolation of the sparse features onto the dense points over the 3 nearest sparse points
+    (square_distance, pointnet2.py:14-33), concatenated behind the skip features, then [conv1 + BN + ReLU] x L."""
+
+    def __init__(self, in_channel, mlp, state_dict, device=None):
+        self.mlp = _SharedMLP(state_dict, len(mlp), device=device)
+        assert self.mlp.dims[0] == in_channel and list(self.mlp.dims[1:]) == list(mlp), (self.mlp.dims, in_channel, mlp)
+
+    def forward(self, xyz1, xyz2, points1, points2, return_nn=False):
+        x1, x2 = _f32(xyz1.permute(0, 2, 1)), _f32(xyz2.permute(0, 2, 1))
+        p2 = _f32(points2.permute(0, 2, 1))
+        p1 = None if points1 is None else _f32(points1.permute(0, 2, 1))
+        B, N, _ = x1.shape
+        S, D2 = p2.shape[1], p2.shape[2]
+        D1 = 0 if p1 is None else p1.shape[2]
+        ctx = _ctx(x1)
+        idx = w = None
+        if S == 1:
+            interp = p2.repeat(1, N, 1)
+            feat = interp if p1 is None else torch.cat([p1, interp], dim=-1)
+        else:
+            feat = torch.empty((B, N, D1 + D2), dtype=torch.float32, device=x1.device)
+            idx = torch.empty((B, N, 3), dtype=torch.int32, device=x1.device)
+            w = torch.empty((B, N, 3), dtype=torch.float32, device=x1.device)
+            ctx.check(ctx.lib.cg_three_interp_dev(ctx.h, _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(p1), D1, _lib.ptr(p2), D2,
+                                                  B, N, S, _lib.ptr(feat), _lib.ptr(idx), _lib.ptr(w)))
+        feat = feat.contiguous()
+        out = torch.empty((B, N, self.mlp.dims[-1]), dtype=torch.float32, device=x1.device)
+        ctx.check(ctx.lib.cg_shared_mlp_dev(self.mlp.h, _lib.ptr(feat), B * N, _lib.ptr(out)))
+        out = out.permute(0, 2, 1)
+        return (out, idx.long(), w) if return_nn else out
+
+    __call__ = forward

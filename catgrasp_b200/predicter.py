@@ -39,17 +39,55 @@ def _load_artifacts(artifact_dir, cfg_name):
     return cfg
 
 
-def draw_subsample_ids(M, n_pts, count=None):
-    """The reference's per-sample index draw (dataset_grasp.py:72-73, dataset_nunocs.py:43-44):
-    ``np.random.choice(np.arange(M), size=n_pts, replace=M < n_pts)`` from the GLOBAL numpy RNG,
-    once per candidate, in candidate order."""
+def draw_subsample_ids_numpy(M, n_pts, count):
+    """The draw exactly as the reference makes it: one np.random.choice per candidate (kept as the pin for the C path)."""
     replace = M < n_pts
     pop = np.arange(M)
-    if count is None:
-        return np.random.choice(pop, size=(n_pts), replace=replace).astype(np.int32)
     out = np.empty((count, n_pts), dtype=np.int32)
     for i in range(count):
         out[i] = np.random.choice(pop, size=(n_pts), replace=replace)
+    return out
+
+
+class _LegacyDraw:
+    """Bit-identical continuation of numpy's GLOBAL legacy generator in C (cg_host_legacy_choice): take the MT19937
+    state once, draw any number of candidates (possibly in chunks, from a worker thread), put the advanced state back."""
+
+    def __init__(self):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib.load()
+        st = np.random.get_state()
+        assert st[0] == "MT19937"
+        self._rest = (st[3], st[4])
+        self.key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+        self.pos = C.c_int32(int(st[2]))
+
+    def draw(self, M, n_pts, count, out=None, nthreads=0):
+        C = self._C
+        if out is None:
+            out = np.empty((count, n_pts), dtype=np.int32)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        rc = self._lib.cg_host_legacy_choice(C.c_void_p(self.key.ctypes.data), C.byref(self.pos), C.c_int64(M),
+                                             C.c_int32(n_pts), C.c_int32(count), C.c_void_p(ptr), C.c_int32(nthreads))
+        if rc != 0:
+            raise ValueError(f"cg_host_legacy_choice({M}, {n_pts}, {count}) failed with {rc}")
+        return out
+
+    def commit(self):
+        np.random.set_state(("MT19937", self.key, int(self.pos.value), self._rest[0], self._rest[1]))
+
+
+def draw_subsample_ids(M, n_pts, count=None):
+    """The reference's per-sample index draw (dataset_grasp.py:72-73, dataset_nunocs.py:43-44):
+    ``np.random.choice(np.arange(M), size=n_pts, replace=M < n_pts)`` from the GLOBAL numpy RNG,
+    once per candidate, in candidate order.  With ``count`` the draws run in C on numpy's own MT19937 state
+    (same indices, same state afterwards -- tests/test_abi_and_host.py compares with numpy itself)."""
+    if count is None:
+        return np.random.choice(np.arange(M), size=(n_pts), replace=M < n_pts).astype(np.int32)
+    d = _LegacyDraw()
+    out = d.draw(M, n_pts, count)
+    d.commit()
     return out
 
 
@@ -71,35 +109,111 @@ class GraspPredicter:
         print("Load ckpt from {}/best_val.pth.tar".format(artifact_dir))
         self.model = PointNetCls(sd, device=device)
         assert self.model.n_out == n_out, f"checkpoint has {self.model.n_out} classes, config says {n_out}"
+        self.subsample = "host"       # "host": the reference's numpy draw, bit for bit; "device": counter-based draw on the GPU
+        self.chunk = 512              # candidates per pipeline stage (host draw of chunk k+1 overlaps the GPU on chunk k)
+        self._pin = None
 
-    def predict_batch(self, data, grasp_poses, ids=None):
+    def _pinned_ids(self, B, n_pts):
+        import torch
+        need = B * n_pts
+        if self._pin is None or self._pin.numel() < need:
+            self._pin = torch.empty((need + need // 4,), dtype=torch.int32).pin_memory()
+        return self._pin[:need].view(B, n_pts)
+
+    def predict_batch(self, data, grasp_poses, ids=None, subsample=None):
         """predicter.py:67-94.  Returns list of [label np.int64, confidence np.float32, probs (n_out,) f32].
 
-        ``data`` is not modified (the reference deep-copies it, :72).  ``ids`` (B,n_pts) overrides the
-        numpy-RNG draw for reproducible comparisons.
+        ``data`` is not modified (the reference deep-copies it, :72).  ``ids`` (B,n_pts) overrides the draw.
+        ``subsample`` (default ``self.subsample``):
+          "host"   -- the reference's per-candidate ``np.random.choice`` (dataset_grasp.py:72-73), bit for bit and
+                      with the same consumption of the global numpy generator; drawn in C in chunks on a worker thread
+                      while the GPU scores the previous chunk;
+          "device" -- a statistically equivalent counter-based draw on the GPU (cg_draw_ids_dev); consumes ONE value
+                      of the global numpy generator (the seed) instead of one shuffle per candidate.  Not the
+                      reference's numbers: use it when throughput matters more than replaying a reference run.
         """
+        import torch
+        from . import _lib
         B = len(grasp_poses)
         if B == 0:
             return []
+        mode = subsample or self.subsample
+        assert mode in ("host", "device"), mode
         xyz = np.asarray(data["cloud_xyz"], dtype=np.float64)
         nrm = np.asarray(data["cloud_normal"], dtype=np.float64)
         valid_mask = xyz[:, 2] >= 0.1                                   # dataset_grasp.py:64
         xyz = np.ascontiguousarray(xyz[valid_mask].reshape(-1, 3))
         nrm = np.ascontiguousarray(nrm[valid_mask].reshape(-1, 3))
-        n_pts = int(self.cfg["n_pts"])
-        if ids is None:
-            ids = draw_subsample_ids(xyz.shape[0], n_pts, count=B)
-        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        M, n_pts = xyz.shape[0], int(self.cfg["n_pts"])
         poses = np.ascontiguousarray(np.asarray(grasp_poses, dtype=np.float64).reshape(B, 4, 4))
-        mean = np.ascontiguousarray(self.cfg["mean"].reshape(-1)) if "mean" in self.cfg else None
-        std = np.ascontiguousarray(self.cfg["std"].reshape(-1)) if "std" in self.cfg else None
-        probs, _ = self.model.graspq_host(xyz, nrm, poses, ids, mean, std)
-        out = []
-        for b in range(B):                                              # predicter.py:87-91
-            cur_pred = probs[b]
-            pred_label = cur_pred.argmax()
-            out.append([pred_label, cur_pred[pred_label], cur_pred])
-        return out
+        net, dev = self.model, self.model.device
+        with torch.cuda.device(dev):
+            d_xyz, d_nrm = torch.from_numpy(xyz).to(dev), torch.from_numpy(nrm).to(dev)
+            d_pose = torch.from_numpy(poses).to(dev)
+            d_mean = torch.from_numpy(np.ascontiguousarray(self.cfg["mean"].reshape(-1))).to(dev) if "mean" in self.cfg else None
+            d_std = torch.from_numpy(np.ascontiguousarray(self.cfg["std"].reshape(-1))).to(dev) if "std" in self.cfg else None
+            d_probs = torch.empty((B, net.n_out), dtype=torch.float32, device=dev)
+            d_label = torch.empty((B,), dtype=torch.int32, device=dev)
+
+            def run(engine_override=None):
+                if ids is not None or mode == "device":
+                    if ids is not None:
+                        d_ids = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)).to(dev)
+                    else:
+                        d_ids = net.draw_ids_dev(M, n_pts, B, seed=self._device_seed)
+                    net.graspq_dev(d_xyz, d_nrm, d_pose, d_ids, d_mean, d_std, out=(d_probs, d_label))
+                    return
+                # bit-parity mode: C continuation of numpy's generator on a worker thread, chunk by chunk
+                import queue
+                import threading
+                h_ids = self._pinned_ids(B, n_pts)
+                draw = self._draw
+                bounds = [(lo, min(B, lo + self.chunk)) for lo in range(0, B, self.chunk)]
+                q = queue.Queue()
+
+                def producer():
+                    try:
+                        for lo, hi in bounds:
+                            if not self._drawn:
+                                draw.draw(M, n_pts, hi - lo, out=h_ids[lo:hi])
+                            q.put((lo, hi))
+                    except Exception as e:   # surfaces in the consumer
+                        q.put(e)
+                t = threading.Thread(target=producer, daemon=True)
+                t.start()
+                d_ids = torch.empty((B, n_pts), dtype=torch.int32, device=dev)
+                for _ in bounds:
+                    item = q.get()
+                    if isinstance(item, Exception):
+                        raise item
+                    lo, hi = item
+                    d_ids[lo:hi].copy_(h_ids[lo:hi], non_blocking=True)
+                    net.graspq_dev(d_xyz, d_nrm, d_pose[lo:hi], d_ids[lo:hi], d_mean, d_std,
+                                   out=(d_probs[lo:hi], d_label[lo:hi]))
+                t.join()
+                self._drawn = True
+
+            if ids is None and mode == "device":
+                self._device_seed = int(np.random.randint(0, 2 ** 63 - 1, dtype=np.int64))
+            if ids is None and mode == "host":
+                self._draw, self._drawn = _LegacyDraw(), False
+            run()
+            probs = d_probs.cpu().numpy()
+            if net.ctx.get_engine() >= 2 and net.ctx.fp16_overflow():
+                # the fast engines clamp the 128->1024 layer's inputs to the fp16 range: redo on the near-fp32 engine
+                print("GraspPredicter: activation beyond the fp16 range, re-running on engine 1 (tcgen05 bf16 hi/lo x3)")
+                eng = net.ctx.get_engine()
+                net.ctx.set_engine(1)
+                try:
+                    run()
+                    probs = d_probs.cpu().numpy()
+                finally:
+                    net.ctx.set_engine(eng)
+            if ids is None and mode == "host":
+                self._draw.commit()
+        labels = probs.argmax(1)                                         # predicter.py:87-91
+        conf = probs[np.arange(B), labels]
+        return [[l, c, p] for l, c, p in zip(labels, conf, probs)]
 
 
 class NunocsPredicter:

@@ -396,3 +396,22 @@ def make_filter_case(seed, G, S, scale=(1, 1, 1), n_points=2400):
     poses_can = np.stack([inv @ p for p in poses])          # canonical_to_cam * pose_can == the camera-frame pose
     g = make_gripper_proxy()
     return p1, p2, poses_can, np.stack(sym), nocs_pose, canonical_to_nocs, g
+
+
+def make_mlp_state_dict(dims, seed=0, conv2d=True):
+    """Seeded weights of a PointNet++ shared-MLP stack in the upstream module layout: mlp_convs.{i} (Conv2d/Conv1d k=1)
+    + mlp_bns.{i} with randomised running statistics (same ranges as make_state_dict)."""
+    import torch
+    rng = np.random.RandomState(seed)
+    sd = OrderedDict()
+    for i in range(len(dims) - 1):
+        cin, cout = dims[i], dims[i + 1]
+        bound = 1.0 / np.sqrt(cin)
+        shp = (cout, cin, 1, 1) if conv2d else (cout, cin, 1)
+        sd[f"mlp_convs.{i}.weight"] = rng.uniform(-bound, bound, size=shp).astype(np.float32)
+        sd[f"mlp_convs.{i}.bias"] = rng.uniform(-bound, bound, size=(cout,)).astype(np.float32)
+        sd[f"mlp_bns.{i}.weight"] = rng.uniform(0.5, 1.5, size=(cout,)).astype(np.float32)
+        sd[f"mlp_bns.{i}.bias"] = rng.normal(0, 0.1, size=(cout,)).astype(np.float32)
+        sd[f"mlp_bns.{i}.running_mean"] = rng.normal(0, 0.2, size=(cout,)).astype(np.float32)
+        sd[f"mlp_bns.{i}.running_var"] = rng.uniform(0.5, 1.5, size=(cout,)).astype(np.float32)
+    return OrderedDict((k, torch.from_numpy(v)) for k, v in sd.items())

@@ -116,6 +116,30 @@ int cg_graspq_forward_dev(cg_net *net,
                           const double *mean, const double *std,
                           float *out_probs, int32_t *out_label);
 
+/* The per-candidate point-subset draw of GraspDataset.transform
+ * (dataset_grasp.py:72-73: np.random.choice(np.arange(M), size=n_pts,
+ * replace=(M < n_pts)) from the GLOBAL legacy numpy generator, once per
+ * candidate, in candidate order).
+ *
+ * cg_host_legacy_choice (HOST function, no GPU work): the same draw, bit for
+ * bit, without the Python-level call per candidate.  key[624] / *pos are the
+ * MT19937 state of np.random.get_state() (fields 1 and 2); both are advanced
+ * exactly as numpy would advance them, so np.random.set_state() afterwards
+ * leaves the host program on the reference's random stream.  The stream walk
+ * is sequential; the permutations are replayed on `nthreads` host threads
+ * (<= 0: one per core, at most 32).  out: (count, n_pts) int32.
+ *
+ * cg_draw_ids_dev (opt-in, NOT the reference's numbers): a counter-based draw
+ * on the device with the same distribution -- n_pts distinct uniform indices
+ * (keyed Feistel permutation of [0,M), cycle-walked) when M >= n_pts, n_pts
+ * independent uniform indices when M < n_pts.  Candidate b uses the key
+ * (seed, first_candidate + b), so shards of one candidate list draw the same
+ * subsets as the unsharded call.  out_ids: (count, n_pts) int32 on device.   */
+int cg_host_legacy_choice(uint32_t *key, int32_t *pos, int64_t M, int32_t n_pts,
+                          int32_t count, int32_t *out, int32_t nthreads);
+int cg_draw_ids_dev(cg_ctx *ctx, int M, int n_pts, int count, uint64_t seed,
+                    int64_t first_candidate, int32_t *out_ids);
+
 /* PointNetCls / PointNetSeg forward on an already materialised input tensor
  * x : (B,N,6) float32 (device).  Replaces pointnet2.py:289-299 / :316-329.
  *   cls: out_logits (B,n_out) and/or out_probs (B,n_out) (either may be NULL)
@@ -264,6 +288,34 @@ int cg_ball_query_dev(cg_ctx *ctx, float radius2, int nsample,
 int cg_group_points_dev(cg_ctx *ctx, const float *xyz, const float *points,
                         const float *new_xyz, const int32_t *idx,
                         int B, int N, int D, int S, int K, float *out);
+
+
+/* ---- PointNet++ set-abstraction / feature-propagation stacks -----------------------------
+ * The reference ships the primitives above and cites the upstream module family in its model
+ * docstrings (pointnet2.py:274,304); these entry points are that family's
+ * PointNetSetAbstraction / PointNetFeaturePropagation built on the primitives
+ * (sample_and_group, pointnet2.py:101-129; square_distance, :14-33).
+ *
+ * cg_mlp: a stack of nlayers shared (1x1 conv + BatchNorm + ReLU) layers, BN folded by the host:
+ *   dims[nlayers+1] channel counts, Wt_host[i] = [dims[i]][dims[i+1]] k-major fp32, b_host[i] = [dims[i+1]].
+ * Layers whose input width is a multiple of 64 run on tcgen05 (bf16 hi/lo x3, fp32 accumulate) when
+ * there are >= 64 rows; narrower ones (the 3+D input layer) on the FMA kernels.                        */
+typedef struct cg_mlp cg_mlp;
+int  cg_mlp_create(cg_ctx *ctx, int nlayers, const int *dims, const float *const *Wt_host,
+                   const float *const *b_host, cg_mlp **out);
+void cg_mlp_destroy(cg_mlp *mlp);
+/* x (R, dims[0]) -> out (R, dims[nlayers]): the per-row MLP (feature-propagation tail).               */
+int  cg_shared_mlp_dev(cg_mlp *mlp, const float *x, int64_t R, float *out);
+/* grouped (G, K, dims[0]) = output of cg_group_points_dev with G = B*S -> out (G, dims[nlayers]):
+ * per-row MLP over all G*K rows, then max over the K rows of every group (set abstraction).           */
+int  cg_group_mlp_max_dev(cg_mlp *mlp, const float *grouped, int G, int K, float *out);
+/* Feature propagation, interpolation half: for every dense point xyz1[b][n] the 3 nearest of the S
+ * sparse points xyz2[b] (expanded-form distances, ties -> lower index), weights (1/(d+1e-8))/sum, and
+ *   out[b][n] = [points1[b][n] (D1 skip channels, optional) | sum_j w_j * points2[b][idx_j] (D2)]
+ * out (B,N,D1+D2); out_idx (B,N,3) int32 / out_weight (B,N,3) optional (NULL: scratch).  S >= 3.      */
+int  cg_three_interp_dev(cg_ctx *ctx, const float *xyz1, const float *xyz2, const float *points1, int D1,
+                         const float *points2, int D2, int B, int N, int S, float *out,
+                         int32_t *out_idx, float *out_weight);
 
 #ifdef __cplusplus
 }

@@ -235,3 +235,63 @@ def test_host_pose_composition_is_bit_identical_to_the_oracle():
     assert (st == 0).all()
     u = grasp_in_cam_unshifted(poses, sym, nocs_pose, c2n)
     assert np.array_equal(u.view(np.uint32), out.view(np.uint32))
+
+
+# ------------------------------------------------------------------ the subset draw (host half of GraspDataset.transform)
+@pytest.mark.parametrize("M,n_pts,count", [(20000, 1024, 24), (3000, 1024, 40), (2048, 2048, 9), (1024, 1024, 12),
+                                           (700, 1024, 12), (1, 5, 3), (2, 2, 4), (5, 8, 6), (1025, 1024, 7)])
+@pytest.mark.parametrize("nthreads", [1, 0])
+def test_c_legacy_choice_equals_numpy(M, n_pts, count, nthreads):
+    """cg_host_legacy_choice continues numpy's GLOBAL MT19937 stream exactly like the reference's per-candidate
+    ``np.random.choice(np.arange(M), size=n_pts, replace=M < n_pts)`` (dataset_grasp.py:72-73): same indices, and the
+    generator is left in the same state (next uniform AND next gaussian draws agree), single- and multi-threaded."""
+    from catgrasp_b200.predicter import _LegacyDraw, draw_subsample_ids_numpy
+    np.random.seed(123)
+    np.random.rand(3)
+    np.random.randn(1)                      # leaves a cached gaussian in the state tuple
+    ref = draw_subsample_ids_numpy(M, n_pts, count)
+    ref_next = (np.random.rand(4), np.random.randn(3))
+    np.random.seed(123)
+    np.random.rand(3)
+    np.random.randn(1)
+    d = _LegacyDraw()
+    a = d.draw(M, n_pts, count // 2, nthreads=nthreads)          # two chunks: the pipelined predict_batch does this
+    b = d.draw(M, n_pts, count - count // 2, nthreads=nthreads)
+    d.commit()
+    got_next = (np.random.rand(4), np.random.randn(3))
+    assert np.array_equal(np.concatenate([a, b]), ref)
+    assert np.array_equal(ref_next[0], got_next[0]) and np.array_equal(ref_next[1], got_next[1])
+
+
+def test_draw_subsample_ids_wrapper_consumes_like_reference():
+    from catgrasp_b200.predicter import draw_subsample_ids, draw_subsample_ids_numpy
+    np.random.seed(7)
+    ref = draw_subsample_ids_numpy(5000, 256, 33)
+    r2 = np.random.rand(2)
+    np.random.seed(7)
+    got = draw_subsample_ids(5000, 256, count=33)
+    assert np.array_equal(ref, got) and np.array_equal(r2, np.random.rand(2))
+    np.random.seed(8)
+    one = draw_subsample_ids(900, 64)
+    np.random.seed(8)
+    assert np.array_equal(one, np.random.choice(np.arange(900), size=64, replace=False))
+
+
+def test_device_draw_oracle_properties():
+    """oracle/draw_ref.py (the pin of cg_draw_ids_dev): distinct in-range indices without replacement, keys depend on
+    (seed, global candidate index) only -> a shard draws what the unsharded call draws."""
+    from oracle.draw_ref import draw_ids
+    full = draw_ids(20000, 1024, 64, seed=99, first_candidate=0)
+    assert full.min() >= 0 and full.max() < 20000
+    assert all(len(set(r.tolist())) == 1024 for r in full)
+    part = draw_ids(20000, 1024, 16, seed=99, first_candidate=32)
+    assert np.array_equal(part, full[32:48])
+    assert not np.array_equal(full[0], full[1])
+    assert not np.array_equal(draw_ids(20000, 1024, 2, seed=100), full[:2])
+    rep = draw_ids(700, 1024, 8, seed=1)
+    assert rep.min() >= 0 and rep.max() < 700
+    perm = draw_ids(1024, 1024, 3, seed=5)
+    assert all(sorted(r.tolist()) == list(range(1024)) for r in perm)        # M == n_pts: a permutation
+    cnt = np.bincount(draw_ids(20000, 1024, 2048, seed=42).ravel(), minlength=20000)
+    e = 2048 * 1024 / 20000
+    assert 0.85 < ((cnt - e) ** 2 / e).sum() / 19999 < 1.1                   # chi2 / dof ~ (1 - n/M)

@@ -805,3 +805,71 @@ def test_grasp_affordance_vs_reference_run(cuda, golden_dir):
     assert np.abs(p[ok] - po[ok]).max() < 1e-12
     with pytest.raises(RuntimeError):
         compute_grasp_affordance(poses[:1], fmig, down, down_n, full, affordance, boxes, [[1, 0, 0], [0, -1, 0]], 0.005)
+
+
+# ------------------------------------------------------------------ subset draws (round 2)
+@pytest.mark.parametrize("M,n_pts,count", [(20000, 1024, 96), (3000, 1024, 17), (1024, 1024, 5), (700, 1024, 9), (1, 1, 4),
+                                           (40000, 2048, 8)])
+def test_device_draw_vs_oracle(cls_net, M, n_pts, count):
+    """cg_draw_ids_dev == oracle/draw_ref.py bit for bit (integer work), including a non-zero first candidate."""
+    from oracle.draw_ref import draw_ids
+    net, _ = cls_net
+    got = net.draw_ids_dev(M, n_pts, count, seed=0x1234_5678_9abc, first_candidate=5).cpu().numpy()
+    assert np.array_equal(got, draw_ids(M, n_pts, count, 0x1234_5678_9abc, 5))
+
+
+def test_device_draw_statistics(cuda, tmp_path):
+    """subsample="device" is NOT the reference's random stream (documented) but the same distribution:
+    (1) every candidate gets n_pts distinct in-range indices; (2) pooled index frequencies are uniform (chi-square);
+    (3) the grasp-Q expectation p_G = sum_k k p_k / 10 (run_grasp_simulation.py:311) of device-drawn subsets is
+    distributed like that of numpy-drawn subsets (two-sample KS test over 512 candidates, p > 1e-3);
+    (4) it consumes exactly one value of the global numpy generator and is reproducible under np.random.seed."""
+    from scipy import stats
+    from catgrasp_b200.predicter import GraspPredicter
+    from catgrasp_b200.synthetic import make_candidates, make_pile, write_artifacts
+    adir = write_artifacts(str(tmp_path / "artifacts-47"), "cls", n_pts=512, seed=0, logit_gain=6.0)
+    gp = GraspPredicter("nut", artifact_dir=adir)
+    scene = make_pile(6000, n_objects=4, seed=31)
+    data = {"cloud_xyz": scene["cloud_xyz"], "cloud_normal": scene["cloud_normal"]}
+    poses = list(make_candidates(scene["cloud_xyz"], scene["cloud_normal"], 8, seed=32)) * 64       # 8 poses x 64 draws each
+    ids = gp.model.draw_ids_dev(6000, 512, 4096, seed=7).cpu().numpy()
+    assert ids.min() >= 0 and ids.max() < 6000 and all(len(set(r.tolist())) == 512 for r in ids[:256])
+    cnt = np.bincount(ids.ravel(), minlength=6000)
+    e = ids.size / 6000
+    assert 0.8 < ((cnt - e) ** 2 / e).sum() / 5999 < 1.1
+    np.random.seed(1)
+    host = gp.predict_batch(data, poses, subsample="host")
+    np.random.seed(1)
+    dev = gp.predict_batch(data, poses, subsample="device")
+    after = np.random.rand()
+    np.random.seed(1)
+    dev2 = gp.predict_batch(data, poses, subsample="device")
+    assert all(np.array_equal(a[2], b[2]) for a, b in zip(dev, dev2))
+    np.random.seed(1)
+    np.random.randint(0, 2 ** 63 - 1, dtype=np.int64)
+    assert np.random.rand() == after                                  # one draw consumed
+    pg = lambda out: np.array([(np.arange(10) * o[2]).sum() / 10 for o in out]).reshape(64, 8)   # noqa: E731
+    ph, pd = pg(host), pg(dev)
+    for k in range(8):                                                # per pose: same sampling distribution of p_G
+        assert stats.ks_2samp(ph[:, k], pd[:, k]).pvalue > 1e-3, k
+    assert np.abs(ph.mean(0) - pd.mean(0)).max() < 4 * (ph.std(0).max() / 8 + 1e-6)
+
+
+def test_predict_batch_pipeline_chunks_equal_single_call(cuda, golden_dir, tmp_path):
+    """The pipelined host draw (C continuation of numpy's MT19937 on a worker thread, chunk by chunk) returns the
+    reference run's probabilities and leaves numpy's generator where the reference leaves it, for any chunk size."""
+    from catgrasp_b200.predicter import GraspPredicter
+    from catgrasp_b200.synthetic import write_artifacts
+    g = np.load(os.path.join(golden_dir, "host_predict_batch.npz"))
+    adir = write_artifacts(str(tmp_path / "artifacts-47"), "cls", n_pts=1024, seed=int(g["artifact_seed"]),
+                           logit_gain=float(g["logit_gain"]))
+    gp = GraspPredicter("nut", artifact_dir=adir)
+    for chunk in (5, 1, 512):
+        gp.chunk = chunk
+        for tag in ("big", "small"):
+            data = {"cloud_xyz": g[f"{tag}_cloud_xyz"].astype(np.float64), "cloud_normal": g[f"{tag}_cloud_normal"].astype(np.float64)}
+            np.random.seed(0)
+            out = gp.predict_batch(data, list(g[f"{tag}_poses"]))
+            np.testing.assert_array_equal(np.random.rand(2), g[f"{tag}_next_rand"])
+            np.testing.assert_array_equal([o[0] for o in out], g[f"{tag}_labels"])
+            assert np.abs(np.stack([o[2] for o in out]) - g[f"{tag}_probs"]).max() < PROB_TOL
