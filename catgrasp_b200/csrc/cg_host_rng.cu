@@ -186,3 +186,22 @@ extern "C" int cg_host_legacy_choice(uint32_t *key, int32_t *pos, int64_t M, int
   *pos = g.pos;
   return CG_OK;
 }
+
+// Advance the generator over `count` candidates without producing indices (a rank that scores candidates [lo, hi) of a
+// list still has to leave numpy's generator where the reference's full loop leaves it).
+extern "C" int cg_host_legacy_skip(uint32_t *key, int32_t *pos, int64_t M, int32_t n_pts, int32_t count) {
+  if (!key || !pos || M <= 0 || M >= (1ll << 31) || n_pts <= 0 || count < 0 || *pos < 0 || *pos > MT_N) return CG_EINVAL;
+  Mt g{key, *pos};
+  if (M < n_pts) {
+    const uint32_t rng = (uint32_t)(M - 1);
+    const uint32_t mask = mask_of(rng);
+    if (rng != 0)
+      for (int64_t i = 0; i < (int64_t)count * n_pts; i++)
+        while ((g.next() & mask) > rng) {
+        }
+  } else {
+    for (int c = 0; c < count; c++) shuffle_skip(g, M);
+  }
+  *pos = g.pos;
+  return CG_OK;
+}

@@ -26,6 +26,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "cg_tc_ptx.cuh"
 #include "cg_trunk_common.cuh"
 
@@ -34,11 +36,11 @@ using namespace cg_trunk;
 using namespace cg_ptx;
 
 constexpr int NFRONT = 8;
-constexpr int NMAXW = 4;
-constexpr int PROD_WARP = NFRONT + NMAXW;   // 12
-constexpr int MMA_WARP = PROD_WARP + 1;     // 13
-constexpr int AUX_WARP = MMA_WARP + 1;      // 14
-constexpr int NTP = (AUX_WARP + 1) * 32;    // 480 threads
+constexpr int NMAXW = 8;
+constexpr int PROD_WARP = NFRONT + NMAXW;   // 16
+constexpr int MMA_WARP = PROD_WARP + 1;     // 17
+constexpr int AUX_WARP = MMA_WARP + 1;      // 18
+constexpr int NTP = (AUX_WARP + 1) * 32;    // 608 threads
 constexpr int NFT = NFRONT * 32;            // 256 front threads
 constexpr uint32_t PIECE = 16384;           // [128 rows x 64 x 16-bit] one swizzled K-block
 constexpr uint32_t XA_OFF = 0;              // [hi|lo] 32 KB: X1 (L1 input), then X2 (L2 input) of the same tile
@@ -85,11 +87,21 @@ struct MiscP {
 #define CG_EXP(a, bit) false
 #endif
 
+// developer timeline: clock64 stamps of one steady-state tile of CTA 0 (slot ids are printed by the host side)
+#ifdef CG_EXPERIMENTS
+#define CG_TRACE_AT(cond, slot)                                                     \
+  do {                                                                              \
+    if (a.dbg && blockIdx.x == 0 && (cond)) a.dbg[16 * gridDim.x + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+#else
+#define CG_TRACE_AT(cond, slot) do { } while (0)
+#endif
+
 constexpr size_t SMEM_BYTES_P = MISC_OFF + sizeof(MiscP) + 1024;   // + slack for manual 1024-byte alignment
 static_assert(SMEM_BYTES_P <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
 __device__ __forceinline__ void bar_front() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void bar_max() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_max() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 // split 8 fp32 values into bf16 hi / lo and store them as the two 16-byte chunks of an operand row
 __device__ __forceinline__ void store_hilo8(unsigned char *hi_dst, unsigned char *lo_dst, const float *v) {
@@ -300,6 +312,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       tw = clock64();
       mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
       t_x3 += clock64() - tw;
+      const bool tr = (it == T / 2) && lane == 0;
+      CG_TRACE_AT(tr, 0);
       const bool has_next = it + 1 < T;
       const uint32_t x3c = tmem_base + xb_col(it);
       for (int c = 0; c < NCHUNK; c++) {
@@ -318,6 +332,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           mbar_wait(smem_u32(&S.full_bar[rslot]), rph);
         }
         tc_fence_after();
+        CG_TRACE_AT(tr, 1 + 2 * c);
         const uint32_t d = tmem_base + (uint32_t)buf * 128u;
         if (elect_one()) {
           const uint32_t w_s = ring_s + (uint32_t)rslot * 2 * PIECE;
@@ -334,16 +349,21 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           umma_commit(smem_u32(&S.acc_bar[buf]));
         }
         __syncwarp();
+        CG_TRACE_AT(tr, 2 + 2 * c);
         if (++rslot == NPAIR) { rslot = 0; rph ^= 1u; }
         // front layers of the NEXT tile run in the shadow of this tile's L3 stream
-        if (has_next && c == 1 && has_l1) {
+        if (has_next && c == (CG_EXP(a, 32) ? 2 : 1) && has_l1) {
           tw = clock64();
+          CG_TRACE_AT(tr, 17);
           issue_l1(it + 1);
+          CG_TRACE_AT(tr, 18);
           t_x12 += clock64() - tw;
         }
-        if (has_next && c == (has_l1 ? 3 : 1)) {
+        if (has_next && c == (has_l1 ? (CG_EXP(a, 32) ? 4 : 3) : (CG_EXP(a, 32) ? 2 : 1))) {
           tw = clock64();
+          CG_TRACE_AT(tr, 19);
           issue_l2(it + 1);
+          CG_TRACE_AT(tr, 20);
           t_x12 += clock64() - tw;
         }
       }
@@ -357,9 +377,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     // D3[pt][ch]: TMEM lanes = points.  Each warp owns the 32 lanes of its quarter; a 16x256b load hands every
     // thread 4 points x 16 columns, so the column max is 2 FMNMX3/FMNMX per value + a 3-step exchange (14 shuffles
     // for 64 columns); the four warps meet in the shared running max of the candidate.
-    const int q = warp & 3;
+    const int q = warp & 3, hsel = (warp - NFRONT) >> 2;   // TMEM lane quarter, column half of every 128-channel chunk
     const uint32_t lane_lo = (uint32_t)(q * 32) << 16, lane_hi = (uint32_t)(q * 32 + 16) << 16;
-    const int mt = tid - NFT;   // 0..127
+    const int mt = tid - NFT;   // 0..255
     int b_cur, tile_cur;
     locate(0, b_cur, tile_cur);
     long long m_all = clock64(), m_wait = 0, mw;
@@ -375,9 +395,11 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         mbar_wait(smem_u32(&S.acc_bar[buf]), use & 1u);
         m_wait += clock64() - mw;
         tc_fence_after();
-        const uint32_t col0 = tmem_base + (uint32_t)buf * 128u;
+        const bool trm = (it == T / 2) && tid == NFT;
+        CG_TRACE_AT(trm, 24 + 3 * c);
+        const uint32_t col0 = tmem_base + (uint32_t)buf * 128u + (uint32_t)hsel * 64u;
         uint32_t ra[32], rb[32];
-        float r0[2], r1[2];
+        float r0[2];
         if (CG_EXP(a, 2)) {   // timing experiment: no TMEM reads, no reduction
           tc_fence_before();
           __syncwarp();
@@ -387,20 +409,16 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         tmem_ld_16x256b_x8(col0 + lane_lo, ra);
         tmem_ld_16x256b_x8(col0 + lane_hi, rb);
         tmem_ld_wait();
-        colmax64_reduce(ra, rb, lane, r0);
-        tmem_ld_16x256b_x8(col0 + 64u + lane_lo, ra);
-        tmem_ld_16x256b_x8(col0 + 64u + lane_hi, rb);
-        tmem_ld_wait();
-        // the accumulator is in registers: hand it back before reducing the second half
+        // this warp's part of the accumulator is in registers: hand it back before reducing
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&S.accfree_bar[buf]));
-        colmax64_reduce(ra, rb, lane, r1);
-        uint32_t *g = gm + c * 128 + 2 * lane;
+        CG_TRACE_AT(trm, 25 + 3 * c);
+        colmax64_reduce(ra, rb, lane, r0);
+        uint32_t *g = gm + c * 128 + hsel * 64 + 2 * lane;
         atomicMax(g, cg_f2key(r0[0]));
         atomicMax(g + 1, cg_f2key(r0[1]));
-        atomicMax(g + 64, cg_f2key(r1[0]));
-        atomicMax(g + 65, cg_f2key(r1[1]));
+        CG_TRACE_AT(trm, 26 + 3 * c);
       }
       if (b_next != b_cur) {
         // last tile of this candidate inside the CTA's range: fold the running max into the global feature
@@ -432,20 +450,32 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     // dependent global loads ids -> cloud row are off the critical path between two tiles)
     double rx[6];
     float rv[6];
-    auto prefetch = [&](int it) {
+    int id_next = 0;   // scene-point index of this thread's point two tiles ahead (the ids load is one more tile ahead
+                       // of the dependent cloud-row loads, so neither ever stalls the front pipeline)
+    auto prefetch_id = [&](int it) {
+      if (a.in.x_direct || it >= T) return;
       int b, tile;
       locate(it, b, tile);
       int n = tile * TP + p;
       if (n >= N) n = N - 1;   // duplicate a valid point: cannot change a max
+      id_next = a.in.ids ? __ldg(a.in.ids + (size_t)b * N + n) : n;
+    };
+    // rows of local tile `it` (its id was fetched by prefetch_id(it) earlier); then start the id load of tile it + 1
+    auto prefetch = [&](int it) {
       if (a.in.x_direct) {
+        int b, tile;
+        locate(it, b, tile);
+        int n = tile * TP + p;
+        if (n >= N) n = N - 1;
         const float *xr = a.in.x_direct + ((size_t)b * N + n) * 6;
 #pragma unroll
         for (int k = 0; k < 6; k++) rv[k] = xr[k];
       } else {
-        const int id = a.in.ids ? a.in.ids[(size_t)b * N + n] : n;
+        const int id = id_next;
         const double *px = a.in.cloud_xyz + (size_t)id * 3;
         const double *pn = a.in.cloud_nrm + (size_t)id * 3;
         rx[0] = px[0]; rx[1] = px[1]; rx[2] = px[2]; rx[3] = pn[0]; rx[4] = pn[1]; rx[5] = pn[2];
+        prefetch_id(it + 1);
       }
     };
     int b_l0 = -1;   // candidate of the previous layer0 call
@@ -507,6 +537,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
         if (last_of_cand) mbar_arrive(smem_u32(&S.cc_free[slot]));   // every front thread is past its reads of cc[slot]
       }
+      CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 52);
     };
     // L1 epilogue of local tile `it`: D1 -> (bias, ReLU | nothing) -> XA as the L2 input
     auto l1_epilogue = [&](int it) {
@@ -514,6 +545,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
       f_l1 += clock64() - fw1;
       tc_fence_after();
+      CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 53);
       if (CG_EXP(a, 4)) {   // timing experiment: front warps skip their math
         tc_fence_before();
         bar_front();
@@ -545,9 +577,11 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       fence_proxy_async();
       bar_front();
       if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
+      CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 54);
     };
 
     // ---- prologue: front layers of the first tile ----
+    prefetch_id(0);
     prefetch(0);
     layer0(0);
     if (T > 1) prefetch(1);
@@ -560,6 +594,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       mbar_wait(smem_u32(&S.l2_bar), (uint32_t)it & 1u);
       f_l2 += clock64() - fw;
       tc_fence_after();
+      CG_TRACE_AT(tid == 0 && it == T / 2, 48);
+      CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 55);
       if (CG_EXP(a, 4)) {
         tc_fence_before();
         bar_front();
@@ -606,10 +642,13 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       tc_fence_before();
       bar_front();
       if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
+      CG_TRACE_AT(tid == 0 && it == T / 2, 49);
+      CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 56);
       // B. 6 -> 64 of the NEXT tile (inputs were prefetched a tile ago)
       if (has_next) {
         layer0(it + 1);
         if (it + 2 < T) prefetch(it + 2);   // loads stay in flight across the waits below
+        CG_TRACE_AT(tid == 0 && it == T / 2, 50);
       }
       // D. L1 epilogue of the next tile
       if (has_next && has_l1) l1_epilogue(it + 1);
@@ -683,8 +722,8 @@ int cg_trunk_launch_p(cg_ctx *ctx, const cg_trunk_args &a) {
   aa.exp_flags = exp_flags;
   unsigned long long *d_dbg = nullptr;
   if (debug) {
-    CG_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)grid * 128));
-    CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)grid * 128, ctx->stream));
+    CG_CUDA(ctx, cudaMalloc(&d_dbg, (size_t)grid * 128 + 64 * 8));
+    CG_CUDA(ctx, cudaMemsetAsync(d_dbg, 0, (size_t)grid * 128 + 64 * 8, ctx->stream));
     aa.dbg = d_dbg;
   }
 #endif
@@ -692,8 +731,8 @@ int cg_trunk_launch_p(cg_ctx *ctx, const cg_trunk_args &a) {
   CG_LAUNCH_CHECK(ctx);
 #ifdef CG_EXPERIMENTS
   if (debug) {
-    std::vector<unsigned long long> h((size_t)grid * 16);
-    CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, (size_t)grid * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> h((size_t)grid * 16 + 64);
+    CG_CUDA(ctx, cudaMemcpyAsync(h.data(), d_dbg, (size_t)grid * 128 + 64 * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_dbg);
     double s[16] = {0};
@@ -704,6 +743,25 @@ int cg_trunk_launch_p(cg_ctx *ctx, const cg_trunk_args &a) {
             "max total %.0f acc-wait %.0f | front total %.0f l2-wait %.0f l1-wait %.0f cycles\n",
             exp_flags, grid, tiles, s[0] / tiles, s[1] / tiles, s[4] / tiles, s[2] / tiles, s[3] / tiles, s[6] / tiles, s[7] / tiles,
             s[8] / tiles, s[9] / tiles, s[10] / tiles);
+    {
+      const unsigned long long *tr = h.data() + (size_t)grid * 16;
+      const long long t0 = (long long)tr[0];
+      static const char *names[64] = {"M x3(it) ready", "M c0 waits done", "M c0 issued", "M c1 waits done", "M c1 issued", "M c2 waits done",
+        "M c2 issued", "M c3 waits done", "M c3 issued", "M c4 waits done", "M c4 issued", "M c5 waits done", "M c5 issued",
+        "M c6 waits done", "M c6 issued", "M c7 waits done", "M c7 issued", "M L1(it+1) begin", "M L1(it+1) issued",
+        "M L2(it+1) begin", "M L2(it+1) issued", "", "", "",
+        "X c0 acc ready", "X c0 freed", "X c0 reduced", "X c1 acc ready", "X c1 freed", "X c1 reduced", "X c2 acc ready", "X c2 freed",
+        "X c2 reduced", "X c3 acc ready", "X c3 freed", "X c3 reduced", "X c4 acc ready", "X c4 freed", "X c4 reduced", "X c5 acc ready",
+        "X c5 freed", "X c5 reduced", "X c6 acc ready", "X c6 freed", "X c6 reduced", "X c7 acc ready", "X c7 freed", "X c7 reduced",
+        "F D2(it) ready", "F x3(it) arrived", "F layer0(it+1)+prefetch done", "", "F x1(it+1) arrived", "F D1(it+1) ready",
+        "F x2(it+1) arrived", "F D2(it+1) ready", "F x3(it+1) arrived", "", "", "", "", "", "", ""};
+      fprintf(stderr, "[trunk_p trace] CTA 0, tile T/2, cycles relative to 'M x3(it) ready':\n");
+      std::vector<std::pair<long long, int>> ev;
+      for (int i = 0; i < 64; i++)
+        if (tr[i] && names[i][0]) ev.push_back({(long long)tr[i] - t0, i});
+      std::sort(ev.begin(), ev.end());
+      for (auto &e : ev) fprintf(stderr, "[trunk_p trace] %8lld  %s\n", e.first, names[e.second]);
+    }
   }
 #endif
   return CG_OK;

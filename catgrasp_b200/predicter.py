@@ -74,6 +74,13 @@ class _LegacyDraw:
             raise ValueError(f"cg_host_legacy_choice({M}, {n_pts}, {count}) failed with {rc}")
         return out
 
+    def skip(self, M, n_pts, count):
+        C = self._C
+        rc = self._lib.cg_host_legacy_skip(C.c_void_p(self.key.ctypes.data), C.byref(self.pos), C.c_int64(M),
+                                           C.c_int32(n_pts), C.c_int32(count))
+        if rc != 0:
+            raise ValueError(f"cg_host_legacy_skip({M}, {n_pts}, {count}) failed with {rc}")
+
     def commit(self):
         np.random.set_state(("MT19937", self.key, int(self.pos.value), self._rest[0], self._rest[1]))
 
@@ -120,7 +127,7 @@ class GraspPredicter:
             self._pin = torch.empty((need + need // 4,), dtype=torch.int32).pin_memory()
         return self._pin[:need].view(B, n_pts)
 
-    def predict_batch(self, data, grasp_poses, ids=None, subsample=None):
+    def predict_batch(self, data, grasp_poses, ids=None, subsample=None, shard=None):
         """predicter.py:67-94.  Returns list of [label np.int64, confidence np.float32, probs (n_out,) f32].
 
         ``data`` is not modified (the reference deep-copies it, :72).  ``ids`` (B,n_pts) overrides the draw.
@@ -131,12 +138,18 @@ class GraspPredicter:
           "device" -- a statistically equivalent counter-based draw on the GPU (cg_draw_ids_dev); consumes ONE value
                       of the global numpy generator (the seed) instead of one shuffle per candidate.  Not the
                       reference's numbers: use it when throughput matters more than replaying a reference run.
+        ``shard=(lo, hi)`` scores only candidates [lo, hi) of the list and returns their (hi-lo, n_out) probabilities
+        as a CUDA tensor -- the random stream is consumed for the WHOLE list (the other candidates' draws are skipped in
+        C), so every rank of a sharded call stays on the reference's stream (catgrasp_b200.dist.sharded_predict_batch).
         """
         import torch
         from . import _lib
-        B = len(grasp_poses)
-        if B == 0:
+        B_all = len(grasp_poses)
+        if B_all == 0:
             return []
+        lo_s, hi_s = (0, B_all) if shard is None else (int(shard[0]), int(shard[1]))
+        assert 0 <= lo_s <= hi_s <= B_all
+        B = hi_s - lo_s
         mode = subsample or self.subsample
         assert mode in ("host", "device"), mode
         xyz = np.asarray(data["cloud_xyz"], dtype=np.float64)
@@ -145,8 +158,19 @@ class GraspPredicter:
         xyz = np.ascontiguousarray(xyz[valid_mask].reshape(-1, 3))
         nrm = np.ascontiguousarray(nrm[valid_mask].reshape(-1, 3))
         M, n_pts = xyz.shape[0], int(self.cfg["n_pts"])
-        poses = np.ascontiguousarray(np.asarray(grasp_poses, dtype=np.float64).reshape(B, 4, 4))
+        poses = np.ascontiguousarray(np.asarray(grasp_poses, dtype=np.float64).reshape(B_all, 4, 4)[lo_s:hi_s])
+        if ids is not None:
+            ids = np.asarray(ids)[lo_s:hi_s]
         net, dev = self.model, self.model.device
+        if B == 0:   # an empty shard still consumes the stream like everybody else
+            if ids is None and mode == "device":
+                np.random.randint(0, 2 ** 63 - 1, dtype=np.int64)
+            elif ids is None:
+                d = _LegacyDraw()
+                d.skip(M, n_pts, B_all)
+                d.commit()
+            import torch as _t
+            return _t.empty((0, net.n_out), dtype=_t.float32, device=dev)
         with torch.cuda.device(dev):
             d_xyz, d_nrm = torch.from_numpy(xyz).to(dev), torch.from_numpy(nrm).to(dev)
             d_pose = torch.from_numpy(poses).to(dev)
@@ -160,7 +184,7 @@ class GraspPredicter:
                     if ids is not None:
                         d_ids = torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)).to(dev)
                     else:
-                        d_ids = net.draw_ids_dev(M, n_pts, B, seed=self._device_seed)
+                        d_ids = net.draw_ids_dev(M, n_pts, B, seed=self._device_seed, first_candidate=lo_s)
                     net.graspq_dev(d_xyz, d_nrm, d_pose, d_ids, d_mean, d_std, out=(d_probs, d_label))
                     return
                 # bit-parity mode: C continuation of numpy's generator on a worker thread, chunk by chunk
@@ -173,10 +197,14 @@ class GraspPredicter:
 
                 def producer():
                     try:
+                        if not self._drawn and lo_s > 0:
+                            draw.skip(M, n_pts, lo_s)
                         for lo, hi in bounds:
                             if not self._drawn:
                                 draw.draw(M, n_pts, hi - lo, out=h_ids[lo:hi])
                             q.put((lo, hi))
+                        if not self._drawn and hi_s < B_all:
+                            draw.skip(M, n_pts, B_all - hi_s)
                     except Exception as e:   # surfaces in the consumer
                         q.put(e)
                 t = threading.Thread(target=producer, daemon=True)
@@ -198,7 +226,7 @@ class GraspPredicter:
             if ids is None and mode == "host":
                 self._draw, self._drawn = _LegacyDraw(), False
             run()
-            probs = d_probs.cpu().numpy()
+            probs = None if shard is not None else d_probs.cpu().numpy()
             if net.ctx.get_engine() >= 2 and net.ctx.fp16_overflow():
                 # the fast engines clamp the 128->1024 layer's inputs to the fp16 range: redo on the near-fp32 engine
                 print("GraspPredicter: activation beyond the fp16 range, re-running on engine 1 (tcgen05 bf16 hi/lo x3)")
@@ -206,11 +234,13 @@ class GraspPredicter:
                 net.ctx.set_engine(1)
                 try:
                     run()
-                    probs = d_probs.cpu().numpy()
+                    probs = None if shard is not None else d_probs.cpu().numpy()
                 finally:
                     net.ctx.set_engine(eng)
             if ids is None and mode == "host":
                 self._draw.commit()
+        if shard is not None:
+            return d_probs
         labels = probs.argmax(1)                                         # predicter.py:87-91
         conf = probs[np.arange(B), labels]
         return [[l, c, p] for l, c, p in zip(labels, conf, probs)]

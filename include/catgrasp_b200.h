@@ -137,6 +137,8 @@ int cg_graspq_forward_dev(cg_net *net,
  * subsets as the unsharded call.  out_ids: (count, n_pts) int32 on device.   */
 int cg_host_legacy_choice(uint32_t *key, int32_t *pos, int64_t M, int32_t n_pts,
                           int32_t count, int32_t *out, int32_t nthreads);
+/* advance the generator over `count` candidates without producing their indices (sharded scoring) */
+int cg_host_legacy_skip(uint32_t *key, int32_t *pos, int64_t M, int32_t n_pts, int32_t count);
 int cg_draw_ids_dev(cg_ctx *ctx, int M, int n_pts, int count, uint64_t seed,
                     int64_t first_candidate, int32_t *out_ids);
 

@@ -210,12 +210,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-           "--cpu-sample", "32", "--candidates", "64", "--scene-pts", "2000", "--nunocs-pts", "512", "--n-pts", "256"]
+           "--cpu-sample", "32", "--config", "K1", "--nunocs-pts", "512", "--n-pts", "256"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "candidate grasps scored/sec" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["config"] == "K1" and "PORT" in line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=root, env=env)

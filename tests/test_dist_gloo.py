@@ -44,3 +44,44 @@ def test_allgather_world2_ragged():
         res = [q.get(timeout=120) for _ in range(2)]
         [p.join(timeout=60) for p in procs]
         assert all(ok for _, ok in res), res
+
+
+def _draw_worker(rank, world, B, M, n_pts, port, q):
+    """Host half of dist.sharded_predict_batch: every rank walks numpy's stream for the WHOLE candidate list but only
+    materialises its own shard (skip / draw / skip), then the shards are all-gathered."""
+    import numpy as np
+    from catgrasp_b200.predicter import _LegacyDraw, draw_subsample_ids_numpy
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    np.random.seed(11)
+    ref = draw_subsample_ids_numpy(M, n_pts, B)
+    ref_next = np.random.rand(3)
+    np.random.seed(11)
+    lo, hi = shard_range(B, rank, world)
+    d = _LegacyDraw()
+    d.skip(M, n_pts, lo)
+    mine = d.draw(M, n_pts, hi - lo, nthreads=2)
+    d.skip(M, n_pts, B - hi)
+    d.commit()
+    same_stream = bool(np.array_equal(np.random.rand(3), ref_next))
+    per = (B + world - 1) // world
+    pad = torch.zeros((per, n_pts), dtype=torch.int32)
+    pad[: hi - lo] = torch.from_numpy(mine)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    full = torch.cat(out)[:B].numpy()
+    q.put((rank, bool(np.array_equal(full, ref)) and same_stream))
+    dist.destroy_process_group()
+
+
+def test_sharded_draw_world2_equals_single_process():
+    ctx = mp.get_context("spawn")
+    for B, M, n_pts in ((13, 3000, 256), (9, 300, 512)):
+        q = ctx.Queue()
+        port = 31500 + (os.getpid() + B) % 2000
+        procs = [ctx.Process(target=_draw_worker, args=(r, 2, B, M, n_pts, port, q)) for r in range(2)]
+        [p.start() for p in procs]
+        res = [q.get(timeout=120) for _ in range(2)]
+        [p.join(timeout=60) for p in procs]
+        assert all(ok for _, ok in res), res
