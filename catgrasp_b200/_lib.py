@@ -28,6 +28,7 @@ class FilterParams(C.Structure):
         ("filter_approach_dir_face_camera", C.c_int),
         ("adjust_collision_pose", C.c_int),
         ("sdf_mode", C.c_int),
+        ("sdf_margin", C.c_float),
     ]
 
 
@@ -83,6 +84,7 @@ SIGNATURES = {
     "cg_square_distance_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_index_points_dev": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cg_fps_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "cg_fps_single_cta_dev": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "cg_ball_query_dev": (_i, [_vp, _f, _i, _vp, _vp, _i, _i, _i, _vp]),
     "cg_group_points_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

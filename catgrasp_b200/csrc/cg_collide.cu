@@ -23,6 +23,7 @@ struct cg_sdf {
   float origin[3];
   float res;
   int border_nonneg;   // every cell on the six boundary faces is >= 0 (true for padded grids, make_sdf.py:30)
+  float border_min;    // smallest value on the six boundary faces
 };
 
 namespace {
@@ -147,7 +148,7 @@ __device__ void fold_grid(const float *inv, const SdfView &s, float *out) {
 }
 
 // true iff point x (camera frame) lies inside the posed gripper: sd(G * x) < 0
-__device__ __forceinline__ bool point_hits(const SdfView &s, const float *G, int mode, float x, float y, float z) {
+__device__ __forceinline__ bool point_hits(const SdfView &s, const float *G, int mode, float margin, float x, float y, float z) {
   const float gx = fmaf(G[2], z, fmaf(G[1], y, fmaf(G[0], x, G[9])));
   const float gy = fmaf(G[5], z, fmaf(G[4], y, fmaf(G[3], x, G[10])));
   const float gz = fmaf(G[8], z, fmaf(G[7], y, fmaf(G[6], x, G[11])));
@@ -158,11 +159,11 @@ __device__ __forceinline__ bool point_hits(const SdfView &s, const float *G, int
     if (s.border_nonneg && (gx < 0.f || gy < 0.f || gz < 0.f || gx > (float)(s.nx - 1) || gy > (float)(s.ny - 1) ||
                             gz > (float)(s.nz - 1)))
       return false;
-    return sdf_trilinear(s, gx, gy, gz) < 0.f;
+    return sdf_trilinear(s, gx, gy, gz) < margin;
   }
   bool inb;
   const float sd = sdf_nearest(s, gx, gy, gz, false, &inb);
-  return inb && (sd < 0.f);
+  return inb && (sd < margin);
 }
 
 constexpr int FT = 256;
@@ -176,7 +177,7 @@ struct HitQueue {
   int count[2];
 };
 
-__device__ bool any_point_hits(const SdfView &s, const float *G, int mode, const float *__restrict__ pts, int P,
+__device__ bool any_point_hits(const SdfView &s, const float *G, int mode, float margin, const float *__restrict__ pts, int P,
                                volatile int *flag, HitQueue &Q) {
   // four independent points per thread and iteration (12 loads in flight) -- the loop is latency-bound otherwise;
   // within one j the 256 threads read consecutive points (coalesced 12-byte rows)
@@ -193,7 +194,7 @@ __device__ bool any_point_hits(const SdfView &s, const float *G, int mode, const
         x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
       }
 #pragma unroll
-      for (int j = 0; j < 4; j++) hit = hit || (ok[j] && point_hits(s, G, mode, x[j], y[j], z[j]));
+      for (int j = 0; j < 4; j++) hit = hit || (ok[j] && point_hits(s, G, mode, margin, x[j], y[j], z[j]));
       if (hit) { *flag = 1; break; }
       if (*flag) break;   // another thread already found a collision
     }
@@ -240,7 +241,7 @@ __device__ bool any_point_hits(const SdfView &s, const float *G, int mode, const
     const int n = Q.count[cur];
     if (threadIdx.x == 0) Q.count[cur ^ 1] = 0;      // next chunk's counter; nobody touches it before the barrier below
     bool hit = false;
-    for (int e = threadIdx.x; e < n; e += FT) hit = hit || (sdf_trilinear(s, Q.x[e], Q.y[e], Q.z[e]) < 0.f);
+    for (int e = threadIdx.x; e < n; e += FT) hit = hit || (sdf_trilinear(s, Q.x[e], Q.y[e], Q.z[e]) < margin);
     if (__syncthreads_or(hit)) return true;
     cur ^= 1;
   }
@@ -313,10 +314,10 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
     // head of the background set, then the object set, then the rest of the background.  (`flag` is only ever set by a
     // hit, so it is still clear whenever a later scan starts.)
     const int head = min(P2, 4 * FT);
-    bool coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts, head, &flag, hq);
-    if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, open_pts, P1, &flag, hq);
+    bool coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, head, &flag, hq);
+    if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, prm.sdf_margin, open_pts, P1, &flag, hq);
     if (!coll && P2 > head)
-      coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, encl_pts + 3 * (size_t)head, P2 - head, &flag, hq);
+      coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts + 3 * (size_t)head, P2 - head, &flag, hq);
     if (!coll) { winner = k; break; }
     __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
   }
@@ -339,12 +340,13 @@ __global__ void sdf_lookup_kernel(SdfView s, const float *__restrict__ gc, int P
   }
 }
 
-SdfView make_view(const cg_sdf *s) {
+SdfView make_view(const cg_sdf *s, float margin = 0.f) {
   SdfView v;
   v.grid = s->grid; v.nx = s->nx; v.ny = s->ny; v.nz = s->nz;
   v.ox = s->origin[0]; v.oy = s->origin[1]; v.oz = s->origin[2];
   v.inv_res = 1.0f / s->res;
-  v.border_nonneg = s->border_nonneg;
+  // the out-of-box shortcut stays exact as long as no boundary cell can report a hit: boundary values >= margin
+  v.border_nonneg = (margin <= 0.f) ? s->border_nonneg : (s->border_min >= margin ? 1 : 0);
   return v;
 }
 
@@ -360,11 +362,14 @@ extern "C" int cg_sdf_create(cg_ctx *ctx, const float *grid_host, int nx, int ny
   for (int k = 0; k < 3; k++) s->origin[k] = origin[k];
   const size_t bytes = (size_t)nx * ny * nz * sizeof(float);
   s->border_nonneg = 1;
-  for (int i = 0; i < nx && s->border_nonneg; i++)
-    for (int j = 0; j < ny && s->border_nonneg; j++)
+  s->border_min = 3.0e38f;
+  for (int i = 0; i < nx; i++)
+    for (int j = 0; j < ny; j++)
       for (int k = 0; k < nz; k++) {
         if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1 && k > 0 && k < nz - 1) { k = nz - 2; continue; }   // jump to the far face
-        if (!(grid_host[((size_t)i * ny + j) * nz + k] >= 0.f)) { s->border_nonneg = 0; break; }
+        const float v = grid_host[((size_t)i * ny + j) * nz + k];
+        if (!(v >= 0.f)) s->border_nonneg = 0;
+        if (!(v >= s->border_min)) s->border_min = v;   // NaN counts as "smallest"
       }
   CG_CUDA(ctx, cudaMalloc(&s->grid, bytes));
   CG_CUDA(ctx, cudaMemcpyAsync(s->grid, grid_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -401,9 +406,10 @@ extern "C" int cg_filter_grasp_pose_dev(cg_ctx *ctx, const cg_filter_params *prm
   CG_REQUIRE(ctx, out_status && out_offset && out_poses, "filter: outputs");
   CG_REQUIRE(ctx, prm->sdf_mode == CG_SDF_TRILINEAR || prm->sdf_mode == CG_SDF_NEAREST, "filter: sdf_mode");
   CG_REQUIRE(ctx, (long)G * S < 2147483647L, "filter: too many pairs");
+  CG_REQUIRE(ctx, prm->sdf_margin >= 0.f && prm->sdf_margin < 1.f, "filter: sdf_margin (metres) out of range");
   CG_CUDA(ctx, cudaSetDevice(ctx->device));
-  SdfView vo = make_view(sdf_open);
-  SdfView ve = sdf_enclosed ? make_view(sdf_enclosed) : vo;
+  SdfView vo = make_view(sdf_open, prm->sdf_margin);
+  SdfView ve = sdf_enclosed ? make_view(sdf_enclosed, prm->sdf_margin) : vo;
   filter_kernel<<<(unsigned)((long)G * S), FT, 0, ctx->stream>>>(*prm, grasp_poses, G, symmetry_tfs, S, vo, open_pts,
                                                                  P1, ve, enclosed_pts, P2, out_status, out_offset,
                                                                  out_poses);

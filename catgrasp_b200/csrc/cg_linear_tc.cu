@@ -101,8 +101,11 @@ __global__ void __launch_bounds__(LT, 1) linear_tc_kernel(const float *__restric
                                                           const unsigned char *__restrict__ wimg,
                                                           const float *__restrict__ bias, int N, int relu,
                                                           int bias_row_div, int x_is_keys, float *__restrict__ Y) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked); using the array
+  // directly keeps the accesses in the shared address space (LDS / STS / ATOMS, not generic LD / ST / ATOM)
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char *smem = smem_dyn;
+  if ((static_cast<uint32_t>(__cvta_generic_to_shared(smem)) & 1023u) != 0u) __trap();
   Bars &S = *reinterpret_cast<Bars *>(smem + STAGES * STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * 128, m0 = blockIdx.y * 128;

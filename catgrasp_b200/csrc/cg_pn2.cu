@@ -4,7 +4,11 @@
 // reference's floating-point forms exactly where the result feeds a comparison:
 //   FPS        : direct form  ((dx*dx + dy*dy) + dz*dz), pointnet2.py:71
 //   ball query : expanded form -2*<s,d> + |s|^2 + |d|^2,  pointnet2.py:30-32
+#include <cooperative_groups.h>
+
 #include "cg_common.cuh"
+
+namespace cgr = cooperative_groups;
 
 namespace {
 
@@ -79,6 +83,107 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const float *__restrict__
   }
 }
 
+// Cluster-cooperative FPS: a thread-block cluster (8 CTAs, 16 where the device allows it) per cloud.  Every thread keeps
+// its PPT points AND their running min-distances in registers for the whole kernel, so a round touches no memory
+// except the hand-over of one 24-byte candidate per CTA: warp shuffle -> CTA (shared memory) -> all CTAs of the cluster
+// (distributed shared memory), one cluster barrier per round.  The candidate carries the point's coordinates, so the
+// next round starts without a dependent global load.  Semantics are the reference's (pointnet2.py:54-75): direct-form
+// fp32 distances, strict `dist < distance` update, first (lowest-index) maximum.
+constexpr int FPSC_T = 512;
+constexpr int FPSC_MAXC = 16;
+
+struct FpsCand {
+  float v, x, y, z;
+  int i;
+  int pad[3];
+};
+
+__device__ __forceinline__ bool fps_better(float v, int i, float ov, int oi) { return ov > v || (ov == v && oi < i); }
+
+template <int PPT>
+__global__ void __launch_bounds__(FPSC_T, 1) fps_cluster_kernel(const float *__restrict__ xyz, int N, int npoint,
+                                                                const int32_t *__restrict__ start_idx,
+                                                                int32_t *__restrict__ out_idx) {
+  cgr::cluster_group cluster = cgr::this_cluster();
+  const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+  const int b = blockIdx.x / csize;
+  __shared__ FpsCand rec[2][FPSC_MAXC];    // written by every CTA of the cluster (slot = writer's rank)
+  __shared__ FpsCand wred[FPSC_T / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float *P = xyz + (size_t)b * N * 3;
+  const int Ttot = csize * FPSC_T, gtid = crank * FPSC_T + tid;
+  float px[PPT], py[PPT], pz[PPT], pd[PPT];
+#pragma unroll
+  for (int k = 0; k < PPT; k++) {
+    const int i = gtid + k * Ttot;
+    if (i < N) {
+      px[k] = P[3 * i]; py[k] = P[3 * i + 1]; pz[k] = P[3 * i + 2];
+      pd[k] = 1e10f;                                        // pointnet2.py:65
+    } else {
+      px[k] = py[k] = pz[k] = 0.f;
+      pd[k] = -2.f;                                         // never selected, never updated (d >= 0 > -2 is false for `<`)
+    }
+  }
+  int far = start_idx ? start_idx[b] : 0;                   // :66 (explicit instead of torch.randint)
+  float cx = P[3 * far], cy = P[3 * far + 1], cz = P[3 * far + 2];
+  cluster.sync();                                           // every CTA's shared memory exists before remote writes
+  for (int it = 0; it < npoint; it++) {
+    if (crank == 0 && tid == 0) out_idx[(size_t)b * npoint + it] = far;   // :69
+    if (it == npoint - 1) break;
+    float bv = -1.f, bx = 0.f, by = 0.f, bz = 0.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < PPT; k++) {
+      const float d = sq_direct(px[k], py[k], pz[k], cx, cy, cz);        // :71
+      if (d < pd[k]) pd[k] = d;                                          // :72-73
+      if (pd[k] > bv) { bv = pd[k]; bi = gtid + k * Ttot; bx = px[k]; by = py[k]; bz = pz[k]; }   // k ascending = index ascending
+    }
+    // warp: winner (value, index), then the winner's coordinates from its lane
+    float wv = bv;
+    int wi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (fps_better(wv, wi, ov, oi)) { wv = ov; wi = oi; }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, bi == wi)) - 1;
+    bx = __shfl_sync(0xffffffffu, bx, src); by = __shfl_sync(0xffffffffu, by, src); bz = __shfl_sync(0xffffffffu, bz, src);
+    if (lane == 0) { wred[wid].v = wv; wred[wid].i = wi; wred[wid].x = bx; wred[wid].y = by; wred[wid].z = bz; }
+    __syncthreads();
+    const int buf = it & 1;
+    if (wid == 0) {
+      FpsCand c;
+      c.v = -1.f; c.i = 0x7fffffff; c.x = c.y = c.z = 0.f;
+      if (lane < FPSC_T / 32) c = wred[lane];
+      float v = c.v;
+      int i = c.i;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (fps_better(v, i, ov, oi)) { v = ov; i = oi; }
+      }
+      const int s2 = __ffs(__ballot_sync(0xffffffffu, c.i == i && lane < FPSC_T / 32)) - 1;
+      const float x = __shfl_sync(0xffffffffu, c.x, s2), y = __shfl_sync(0xffffffffu, c.y, s2), z = __shfl_sync(0xffffffffu, c.z, s2);
+      if (lane < csize) {     // lane r delivers this CTA's candidate into CTA r's slot [crank]
+        FpsCand *dst = cluster.map_shared_rank(&rec[buf][crank], lane);
+        dst->v = v; dst->x = x; dst->y = y; dst->z = z; dst->i = i;
+      }
+    }
+    cluster.sync();           // release/acquire: all candidates of this round are visible in every CTA
+    float gv = -1.f;
+    int gi = 0x7fffffff;
+    for (int r = 0; r < csize; r++) {
+      const float ov = rec[buf][r].v;
+      const int oi = rec[buf][r].i;
+      if (fps_better(gv, gi, ov, oi)) { gv = ov; gi = oi; cx = rec[buf][r].x; cy = rec[buf][r].y; cz = rec[buf][r].z; }
+    }
+    far = gi;                                               // :74 torch.max -> first max index
+  }
+  cluster.sync();             // no CTA exits while a peer may still write into its shared memory
+}
+
 // ---------------------------------------------------------- ball query ------
 // One warp per centroid; 32 points per step, ballot + prefix popcount keeps the
 // reference's "nsample smallest indices" order without a sort.
@@ -118,18 +223,29 @@ __global__ void __launch_bounds__(BQ_WARPS * 32) ball_query_kernel(float r2, int
 }
 
 // ------------------------------------------------------ dense helpers ------
-__global__ void square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int B, int S,
-                                       int N, float *__restrict__ out) {
-  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long total = (long)B * S * N;
-  if (t >= total) return;
-  const int n = (int)(t % N);
-  const long bs = t / N;
-  const int b = (int)(bs / S);
-  const float *s = src + bs * 3;
+// (B,S,3) x (B,N,3) -> (B,S,N): a CTA produces a 64 x 256 tile; the 64 source rows and their squared norms sit in
+// shared memory, every thread owns one destination point and streams 64 coalesced stores (the kernel is bound by the
+// S*N*4 output bytes).
+constexpr int SQ_TS = 64, SQ_TN = 256;
+__global__ void __launch_bounds__(SQ_TN) square_distance_kernel(const float *__restrict__ src, const float *__restrict__ dst, int B,
+                                                                int S, int N, float *__restrict__ out) {
+  __shared__ float4 ss[SQ_TS];
+  const int b = blockIdx.z, s0 = blockIdx.y * SQ_TS, n = blockIdx.x * SQ_TN + threadIdx.x;
+  if (threadIdx.x < SQ_TS && s0 + threadIdx.x < S) {
+    const float *s = src + ((size_t)b * S + s0 + threadIdx.x) * 3;
+    ss[threadIdx.x] = make_float4(s[0], s[1], s[2],
+                                  __fadd_rn(__fadd_rn(__fmul_rn(s[0], s[0]), __fmul_rn(s[1], s[1])), __fmul_rn(s[2], s[2])));
+  }
+  __syncthreads();
+  if (n >= N) return;
   const float *d = dst + ((size_t)b * N + n) * 3;
-  const float ss = __fadd_rn(__fadd_rn(__fmul_rn(s[0], s[0]), __fmul_rn(s[1], s[1])), __fmul_rn(s[2], s[2]));
-  out[t] = sq_expanded(s[0], s[1], s[2], ss, d[0], d[1], d[2]);
+  const float dx = d[0], dy = d[1], dz = d[2];
+  const int cnt = min(SQ_TS, S - s0);
+  float *o = out + ((size_t)b * S + s0) * N + n;
+  for (int i = 0; i < cnt; i++) {
+    const float4 s = ss[i];
+    o[(size_t)i * N] = sq_expanded(s.x, s.y, s.z, s.w, dx, dy, dz);
+  }
 }
 
 __global__ void index_points_kernel(const float *__restrict__ points, const int32_t *__restrict__ idx, int B, int N,
@@ -171,9 +287,57 @@ extern "C" int cg_fps_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoin
   if (!ctx) return CG_EINVAL;
   CG_REQUIRE(ctx, xyz && out_idx && B > 0 && N > 0 && npoint > 0, "fps: bad arguments");
   CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  // cluster size: 16 CTAs (non-portable) when the device can co-schedule them, else 8; points per thread in registers
+  static int csize_dev[CG_MAX_DEVICES] = {};
+  if (csize_dev[ctx->device] == 0) {
+    int cs = 8;
+    const void *fns[4] = {(const void *)fps_cluster_kernel<4>, (const void *)fps_cluster_kernel<8>,
+                          (const void *)fps_cluster_kernel<16>, (const void *)fps_cluster_kernel<32>};
+    bool ok16 = true;
+    for (const void *f : fns)
+      if (cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok16 = false;
+    if (ok16) {
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(16); q.blockDim = dim3(FPSC_T);
+      cudaLaunchAttribute at;
+      at.id = cudaLaunchAttributeClusterDimension;
+      at.val.clusterDim.x = 16; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+      q.attrs = &at; q.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, fps_cluster_kernel<8>, &q) == cudaSuccess && ncl >= 1) cs = 16;
+    }
+    cudaGetLastError();
+    csize_dev[ctx->device] = cs;
+  }
+  const int csize = csize_dev[ctx->device];
+  const long per_thread = ((long)N + (long)csize * FPSC_T - 1) / ((long)csize * FPSC_T);
+  CG_REQUIRE(ctx, per_thread <= 32, "fps: N too large (max 32 points per thread x 512 threads x cluster size)");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(B * csize));
+  cfg.blockDim = dim3(FPSC_T);
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = (unsigned)csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  if (per_thread <= 4) CG_CUDA(ctx, cudaLaunchKernelEx(&cfg, fps_cluster_kernel<4>, xyz, N, npoint, start_idx, out_idx));
+  else if (per_thread <= 8) CG_CUDA(ctx, cudaLaunchKernelEx(&cfg, fps_cluster_kernel<8>, xyz, N, npoint, start_idx, out_idx));
+  else if (per_thread <= 16) CG_CUDA(ctx, cudaLaunchKernelEx(&cfg, fps_cluster_kernel<16>, xyz, N, npoint, start_idx, out_idx));
+  else CG_CUDA(ctx, cudaLaunchKernelEx(&cfg, fps_cluster_kernel<32>, xyz, N, npoint, start_idx, out_idx));
+  CG_LAUNCH_CHECK(ctx);
+  return CG_OK;
+}
+
+// the round-1 single-CTA kernel (kept for comparison in scripts/bench_primitives.py)
+extern "C" int cg_fps_single_cta_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoint, const int32_t *start_idx,
+                                     int32_t *out_idx) {
+  if (!ctx) return CG_EINVAL;
+  CG_REQUIRE(ctx, xyz && out_idx && B > 0 && N > 0 && npoint > 0, "fps: bad arguments");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t full = (size_t)N * 16, dist_only = (size_t)N * 4;
   const size_t cap = 220 * 1024;
-  CG_REQUIRE(ctx, dist_only <= cap, "fps: N too large for the shared-memory distance array (max 56320)");
+  CG_REQUIRE(ctx, dist_only <= cap, "fps (single CTA): N too large for the shared-memory distance array (max 56320)");
   static bool attr_set[CG_MAX_DEVICES] = {};   // the attribute is per device
   if (!attr_set[ctx->device]) {
     CG_CUDA(ctx, cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
@@ -192,6 +356,7 @@ extern "C" int cg_ball_query_dev(cg_ctx *ctx, float radius2, int nsample, const 
                                  int B, int N, int S, int32_t *out_idx) {
   if (!ctx) return CG_EINVAL;
   CG_REQUIRE(ctx, xyz && new_xyz && out_idx && B > 0 && N > 0 && S > 0 && nsample > 0, "ball_query: bad arguments");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
   const long warps = (long)B * S;
   ball_query_kernel<<<(unsigned)((warps + BQ_WARPS - 1) / BQ_WARPS), BQ_WARPS * 32, 0, ctx->stream>>>(
       radius2, nsample, xyz, new_xyz, B, N, S, out_idx);
@@ -203,8 +368,10 @@ extern "C" int cg_square_distance_dev(cg_ctx *ctx, const float *src, const float
                                       float *out) {
   if (!ctx) return CG_EINVAL;
   CG_REQUIRE(ctx, src && dst && out && B > 0 && S > 0 && N > 0, "square_distance: bad arguments");
-  const long total = (long)B * S * N;
-  square_distance_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, dst, B, S, N, out);
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  CG_REQUIRE(ctx, B <= 65535 && (S + SQ_TS - 1) / SQ_TS <= 65535, "square_distance: B or S too large for one launch");
+  dim3 grid((N + SQ_TN - 1) / SQ_TN, (S + SQ_TS - 1) / SQ_TS, B);
+  square_distance_kernel<<<grid, SQ_TN, 0, ctx->stream>>>(src, dst, B, S, N, out);
   CG_LAUNCH_CHECK(ctx);
   return CG_OK;
 }
@@ -213,6 +380,7 @@ extern "C" int cg_index_points_dev(cg_ctx *ctx, const float *points, const int32
                                    float *out) {
   if (!ctx) return CG_EINVAL;
   CG_REQUIRE(ctx, points && idx && out && B > 0 && N > 0 && C > 0 && S > 0, "index_points: bad arguments");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
   const long total = (long)B * S * C;
   index_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(points, idx, B, N, C, S, out);
   CG_LAUNCH_CHECK(ctx);
@@ -224,6 +392,7 @@ extern "C" int cg_group_points_dev(cg_ctx *ctx, const float *xyz, const float *p
   if (!ctx) return CG_EINVAL;
   CG_REQUIRE(ctx, xyz && new_xyz && idx && out && B > 0 && N > 0 && S > 0 && K > 0 && D >= 0, "group_points: bad arguments");
   CG_REQUIRE(ctx, D == 0 || points, "group_points: points required when D > 0");
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
   const long total = (long)B * S * K * (3 + D);
   group_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(xyz, points, new_xyz, idx, B, N, D, S, K,
                                                                            out);

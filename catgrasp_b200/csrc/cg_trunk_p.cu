@@ -138,8 +138,12 @@ __device__ __forceinline__ void issue_k64(uint32_t d, uint32_t x_s, uint32_t x_p
 __device__ __forceinline__ uint32_t xb_col(int it) { return 256u + (uint32_t)(it & 1) * 128u; }
 
 __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, int ntiles, int total_tiles) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // The operand tiles need 1024-byte alignment (SWIZZLE_128B atoms).  The kernel has no static shared memory, so the
+  // dynamic window starts at an aligned offset; using the array directly (instead of re-aligning through an integer
+  // cast) keeps every access in the shared address space: LDS / STS / ATOMS instead of generic LD / ST / ATOM.
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char *smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
   unsigned char *xa = smem + XA_OFF, *w1 = smem + W1_OFF;
   MiscP &S = *reinterpret_cast<MiscP *>(smem + MISC_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -259,6 +263,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     }
   } else if (warp == MMA_WARP) {
     // ======================= UMMA issuer: the warp stays converged, one elected lane issues =======================
+    // (Measured: tcgen05.mma issue is synchronous with the tensor pipe -- ~75 cycles per 128x128x16 UMMA in the issuing
+    // thread -- so waits in this thread are pipe bubbles.  A second issuer warp for the L1/L2 layers was tried and was
+    // SLOWER (768 vs 850 TFLOP/s): the front warps' chain then gates the L3 stream through x3 instead of x1/x2.)
     const uint32_t wb = smem_u32(&S.w_bar);
     if (elect_one()) {
       mbar_expect_tx(wb, IMG_W2 + (a.stage1_mode == 1 ? IMG_W1 : 0u));

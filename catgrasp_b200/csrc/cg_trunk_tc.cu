@@ -285,8 +285,11 @@ __global__ void __launch_bounds__(NTC, 1) trunk_tc_kernel(const cg_trunk_args a,
   using L = Lay<TS>;
   constexpr int NSLOT = L::NSLOT;
   constexpr uint32_t D1_COL = L::D1_COL, D2_COL = L::D2_COL;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  // no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked); using the array
+  // directly keeps the accesses in the shared address space (LDS / STS / ATOMS, not generic LD / ST / ATOM)
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  unsigned char *smem = smem_dyn;
+  if ((static_cast<uint32_t>(__cvta_generic_to_shared(smem)) & 1023u) != 0u) __trap();
   unsigned char *x3 = smem + X3_OFF, *xa = smem + XA_OFF, *w1 = smem + W1_OFF;
   Misc &S = *reinterpret_cast<Misc *>(smem + L::MISC_OFF);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -24,6 +24,18 @@ from . import _lib
 _SDF_REGISTRY = {}
 _IK_SOLVER = None
 DEFAULT_SDF_MODE = _lib.CG_SDF_TRILINEAR
+# Which geometry predicate filterGraspPose uses for "the posed gripper touches a scene point":
+#   "sdf"   -- the point lies inside the gripper solid (sd < 0): the predicate of meshpy's Sdf3D.is_any_points_inside;
+#   "voxel" -- sd < octo_resolution * sqrt(3) / 2: conservative stand-in for the reference's FCL mesh-vs-octomap test
+#              (collision_manager.cpp:93-111), where a point occupies a whole voxel cube of side octo_resolution -- every
+#              cube that can touch the gripper surface has its generating point within half a cube diagonal of it.
+# Measured agreement with a restatement of the mesh-vs-voxel semantic: DESIGN.md, X2.
+COLLISION_PREDICATE = "sdf"
+
+
+def voxel_margin(octo_resolution):
+    return float(np.float32(octo_resolution) * np.float32(np.sqrt(3.0) / 2.0))
+
 
 
 def _digest(vertices, faces):
@@ -59,7 +71,7 @@ def _m16(m):
 
 def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_in_grasp,
                           filter_approach_dir_face_camera, adjust_collision_pose, sdf_open, open_pts,
-                          sdf_enclosed, enclosed_pts, sdf_mode=None, device_out=False):
+                          sdf_enclosed, enclosed_pts, sdf_mode=None, device_out=False, sdf_margin=0.0):
     """Array-level entry: returns (status (Q,) u8, offset (Q,) i8, poses (Q,4,4) f32) with Q = G*S."""
     ctx = sdf_open.ctx
     prm = _lib.FilterParams()
@@ -69,6 +81,7 @@ def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_noc
     prm.filter_approach_dir_face_camera = int(bool(filter_approach_dir_face_camera))
     prm.adjust_collision_pose = int(bool(adjust_collision_pose))
     prm.sdf_mode = DEFAULT_SDF_MODE if sdf_mode is None else int(sdf_mode)
+    prm.sdf_margin = float(sdf_margin)
     if isinstance(grasp_poses, torch.Tensor) and grasp_poses.is_cuda:
         dev = grasp_poses.device
         gp = grasp_poses.to(torch.float32).contiguous().reshape(-1, 16)
@@ -151,7 +164,8 @@ def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_tran
         grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform, gripper_in_grasp,
         filter_approach_dir_face_camera, adjust_collision_pose, sdf_open,
         np.asarray(gripper_collision_pts).reshape(-1, 3), sdf_encl,
-        np.asarray(gripper_enclosed_collision_pts).reshape(-1, 3))
+        np.asarray(gripper_enclosed_collision_pts).reshape(-1, 3),
+        sdf_margin=voxel_margin(octo_resolution) if COLLISION_PREDICATE == "voxel" else 0.0)
     keep = status == _lib.CG_ST_ACCEPT
     n_ik = 0
     if filter_ik:

@@ -204,6 +204,12 @@ typedef struct cg_filter_params {
   int   filter_approach_dir_face_camera;
   int   adjust_collision_pose;
   int   sdf_mode;          /* CG_SDF_TRILINEAR or CG_SDF_NEAREST */
+  float sdf_margin;        /* a scene point collides iff sd < sdf_margin (metres).  0 = the SDF predicate of
+                              meshpy/sdf.py:377-389 (point inside the gripper solid).  octo_resolution*sqrt(3)/2 makes
+                              the verdict conservative w.r.t. the reference's mesh-vs-voxel test
+                              (my_cpp/collision_manager.cpp:93-111): every occupied voxel cube of side
+                              octo_resolution that can touch the gripper surface has its generating point within
+                              that distance of the surface.                                                        */
 } cg_filter_params;
 
 int cg_filter_grasp_pose_host(cg_ctx *ctx, const cg_filter_params *prm,
@@ -276,9 +282,15 @@ int cg_square_distance_dev(cg_ctx *ctx, const float *src, const float *dst,
 /* pointnet2.py:35-51  index_points: points (B,N,C), idx (B,S) -> (B,S,C)    */
 int cg_index_points_dev(cg_ctx *ctx, const float *points, const int32_t *idx,
                         int B, int N, int C, int S, float *out);
-/* pointnet2.py:54-75  farthest_point_sample with explicit start indices     */
+/* pointnet2.py:54-75  farthest_point_sample with explicit start indices.
+ * cg_fps_dev: one thread-block cluster per cloud, points + running distances in
+ * registers, one distributed-shared-memory exchange per round (N <= 131072 /
+ * 262144 points for cluster size 8 / 16).  cg_fps_single_cta_dev: the round-1
+ * one-CTA kernel (N <= 56320), kept for comparison.                           */
 int cg_fps_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoint,
                const int32_t *start_idx, int32_t *out_idx);
+int cg_fps_single_cta_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoint,
+                          const int32_t *start_idx, int32_t *out_idx);
 /* pointnet2.py:78-98  query_ball_point (first nsample by index, pad w/ first;
  * an empty ball yields N in every slot, like the reference).  radius2 is
  * float32(radius**2), the threshold torch compares against (:93)            */

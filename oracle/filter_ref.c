@@ -129,19 +129,19 @@ static void fold_grid(const float *inv, const sdf_view *s, float *out) {
 }
 
 /* G = camera frame -> grid coordinates ((x - origin)/res of sdf.py:252-264 folded into the inverse gripper pose) */
-static int point_hits(const sdf_view *s, const float *G, int mode, float x, float y, float z) {
+static int point_hits(const sdf_view *s, const float *G, int mode, float margin, float x, float y, float z) {
   const float gx = fmaf(G[2], z, fmaf(G[1], y, fmaf(G[0], x, G[9])));
   const float gy = fmaf(G[5], z, fmaf(G[4], y, fmaf(G[3], x, G[10])));
   const float gz = fmaf(G[8], z, fmaf(G[7], y, fmaf(G[6], x, G[11])));
-  if (mode == 0) return sdf_trilinear(s, gx, gy, gz) < 0.f;
+  if (mode == 0) return sdf_trilinear(s, gx, gy, gz) < margin;
   int inb;
   const float sd = sdf_nearest(s, gx, gy, gz, 0, &inb);
-  return inb && (sd < 0.f);
+  return inb && (sd < margin);
 }
 
-static int any_hits(const sdf_view *s, const float *inv, int mode, const float *pts, int P) {
+static int any_hits(const sdf_view *s, const float *inv, int mode, float margin, const float *pts, int P) {
   for (int p = 0; p < P; p++)
-    if (point_hits(s, inv, mode, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2])) return 1;
+    if (point_hits(s, inv, mode, margin, pts[3 * p], pts[3 * p + 1], pts[3 * p + 2])) return 1;
   return 0;
 }
 
@@ -153,12 +153,12 @@ int gripper_hits_ref(const float *gripper_in_cam, const float *grid, const int *
   float inv[12], g[12];
   affine_inverse(gripper_in_cam, inv);
   fold_grid(inv, &s, g);
-  return any_hits(&s, g, mode, pts, P);
+  return any_hits(&s, g, mode, 0.f, pts, P);
 }
 
 /* status: 0 accept, 1 approach-direction reject, 3 collision reject; offset: 0..4 or -1 */
-void filter_ref(const float *nocs_pose, const float *canonical_to_nocs, const float *gripper_in_grasp,
-                int filter_dir, int adjust, int sdf_mode, const float *grasp_poses, int G, const float *sym, int S,
+void filter_ref_m(const float *nocs_pose, const float *canonical_to_nocs, const float *gripper_in_grasp,
+                int filter_dir, int adjust, int sdf_mode, float sdf_margin, const float *grasp_poses, int G, const float *sym, int S,
                 const float *grid_open, const int *dims_open, const float *origin_open, float res_open,
                 const float *open_pts, int P1, const float *grid_encl, const int *dims_encl,
                 const float *origin_encl, float res_encl, const float *encl_pts, int P2, int nthreads,
@@ -211,8 +211,8 @@ void filter_ref(const float *nocs_pose, const float *canonical_to_nocs, const fl
       affine_inverse(gic, inv);
       fold_grid(inv, &so, go);
       fold_grid(inv, &se, ge);
-      int coll = any_hits(&so, go, sdf_mode, open_pts, P1);
-      if (!coll && P2 > 0) coll = any_hits(&se, ge, sdf_mode, encl_pts, P2);
+      int coll = any_hits(&so, go, sdf_mode, sdf_margin, open_pts, P1);
+      if (!coll && P2 > 0) coll = any_hits(&se, ge, sdf_mode, sdf_margin, encl_pts, P2);
       if (!coll) { winner = k; break; }
     }
     out_status[q] = (winner >= 0) ? 0 : 3;
@@ -228,4 +228,15 @@ void sdf_lookup_ref(const float *grid, const int *dims, const float *gc, int P, 
     if (mode == 0) out[p] = sdf_trilinear(&s, gc[3 * p], gc[3 * p + 1], gc[3 * p + 2]);
     else { int inb; out[p] = sdf_nearest(&s, gc[3 * p], gc[3 * p + 1], gc[3 * p + 2], 1, &inb); }
   }
+}
+
+/* margin 0: the SDF predicate itself (the form the reference build in oracle/_ref is compared with) */
+void filter_ref(const float *nocs_pose, const float *canonical_to_nocs, const float *gripper_in_grasp, int filter_dir,
+                int adjust, int sdf_mode, const float *grasp_poses, int G, const float *sym, int S, const float *grid_open,
+                const int *dims_open, const float *origin_open, float res_open, const float *open_pts, int P1,
+                const float *grid_encl, const int *dims_encl, const float *origin_encl, float res_encl,
+                const float *encl_pts, int P2, int nthreads, uint8_t *out_status, int8_t *out_offset, float *out_poses) {
+  filter_ref_m(nocs_pose, canonical_to_nocs, gripper_in_grasp, filter_dir, adjust, sdf_mode, 0.f, grasp_poses, G, sym, S,
+               grid_open, dims_open, origin_open, res_open, open_pts, P1, grid_encl, dims_encl, origin_encl, res_encl,
+               encl_pts, P2, nthreads, out_status, out_offset, out_poses);
 }
