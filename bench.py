@@ -589,7 +589,7 @@ def main():
                 "peak_source": f"{peaks['source']} bf16 dense, " + (f"sustained (timed region {ms / 1e3:.1f} s)" if long_region else "burst"),
                 "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
                 "frac_of_sustained_peak": achieved / peaks["bf16_tflops_sustained"],
-                "whole_step_tflops": (FLOP_PER_CAND[N] * value / 1e12) if N in FLOP_PER_CAND else None}
+                "whole_step_tflops_per_gpu": (FLOP_PER_CAND[N] * value / world / 1e12) if N in FLOP_PER_CAND else None}
 
     line = {"metric": "candidate grasps scored/sec", "value": value, "unit": "candidates/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,

@@ -52,6 +52,7 @@ extern "C" void cg_ctx_destroy(cg_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->switch_event) cudaEventDestroy(ctx->switch_event);
   if (ctx->ovf_flag) cudaFree(ctx->ovf_flag);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->io) cudaFree(ctx->io);
@@ -60,17 +61,32 @@ extern "C" void cg_ctx_destroy(cg_ctx *ctx) {
   delete ctx;
 }
 
+// The context's workspaces (ws / io arenas) are reused by consecutive calls.  When the caller moves the context to a
+// different stream, work already enqueued on the previous stream may still be reading them: order the new stream behind
+// the old one with an event (no host synchronisation).
+static int switch_stream(cg_ctx *ctx, cudaStream_t next) {
+  if (next == ctx->stream) return CG_OK;
+  CG_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->switch_event) CG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->switch_event, cudaEventDisableTiming));
+  // the previous stream may be a caller-owned stream that has been destroyed since: its work is complete then, and
+  // recording on a dead handle is an error we can ignore
+  if (cudaEventRecord(ctx->switch_event, ctx->stream) == cudaSuccess)
+    CG_CUDA(ctx, cudaStreamWaitEvent(next, ctx->switch_event, 0));
+  else
+    cudaGetLastError();
+  ctx->stream = next;
+  return CG_OK;
+}
+
 extern "C" int cg_ctx_set_stream(cg_ctx *ctx, void *cuda_stream) {
   if (!ctx) return CG_EINVAL;
   // NULL is a real stream: the CUDA legacy default stream (what torch uses unless told otherwise)
-  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
-  return CG_OK;
+  return switch_stream(ctx, static_cast<cudaStream_t>(cuda_stream));
 }
 
 extern "C" int cg_ctx_use_own_stream(cg_ctx *ctx) {
   if (!ctx) return CG_EINVAL;
-  ctx->stream = ctx->own_stream;
-  return CG_OK;
+  return switch_stream(ctx, ctx->own_stream);
 }
 
 extern "C" int cg_ctx_synchronize(cg_ctx *ctx) {

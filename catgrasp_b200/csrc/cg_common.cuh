@@ -23,6 +23,7 @@ struct cg_ctx {
   int64_t launches = 0;
   // 0 = fp32 SIMT, 1 = tcgen05 bf16 3-pass, 2 = tcgen05 fp16 2-pass, 3 = persistent tcgen05, single fp16 pass (default)
   int engine = 3;
+  cudaEvent_t switch_event = nullptr;   // orders a newly selected stream behind the previous one (shared workspaces)
   uint32_t *ovf_flag = nullptr;   // device word: engine 3 saw a 128->1024 input above the fp16 range (clamped)
   int num_sms = 148;
   // optional event-pair timing of trunk launches (bench roofline)

@@ -5,6 +5,7 @@
 //   FPS        : direct form  ((dx*dx + dy*dy) + dz*dz), pointnet2.py:71
 //   ball query : expanded form -2*<s,d> + |s|^2 + |d|^2,  pointnet2.py:30-32
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "cg_common.cuh"
 
@@ -85,11 +86,12 @@ __global__ void __launch_bounds__(FPS_T, 1) fps_kernel(const float *__restrict__
 
 // Cluster-cooperative FPS: a thread-block cluster (8 CTAs, 16 where the device allows it) per cloud.  Every thread keeps
 // its PPT points AND their running min-distances in registers for the whole kernel, so a round touches no memory
-// except the hand-over of one 24-byte candidate per CTA: warp shuffle -> CTA (shared memory) -> all CTAs of the cluster
-// (distributed shared memory), one cluster barrier per round.  The candidate carries the point's coordinates, so the
+// except the hand-over of one 24-byte candidate per CTA: warp redux -> CTA (shared memory) -> all CTAs of the cluster
+// (distributed shared memory), signalled by remote mbarrier arrivals (release/acquire at cluster scope; a full
+// barrier.cluster per round measured 1.9 us/round, 3x the exchange itself).  The candidate carries the point's coordinates, so the
 // next round starts without a dependent global load.  Semantics are the reference's (pointnet2.py:54-75): direct-form
 // fp32 distances, strict `dist < distance` update, first (lowest-index) maximum.
-constexpr int FPSC_T = 512;
+constexpr int FPSC_T = 256;
 constexpr int FPSC_MAXC = 16;
 
 struct FpsCand {
@@ -98,7 +100,14 @@ struct FpsCand {
   int pad[3];
 };
 
-__device__ __forceinline__ bool fps_better(float v, int i, float ov, int oi) { return ov > v || (ov == v && oi < i); }
+__device__ __forceinline__ uint32_t fps_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// (value desc, index asc) winner of a warp with two redux instructions: distances are >= 0, so their bit patterns order
+// like unsigned integers (-2 marks an unused slot and maps to 0)
+__device__ __forceinline__ void fps_warp_winner(float v, int i, uint32_t &wbits, int &wi) {
+  const uint32_t bits = v < 0.f ? 0u : __float_as_uint(v) + 1u;
+  wbits = __reduce_max_sync(0xffffffffu, bits);
+  wi = (int)__reduce_min_sync(0xffffffffu, bits == wbits ? (uint32_t)i : 0xffffffffu);
+}
 
 template <int PPT>
 __global__ void __launch_bounds__(FPSC_T, 1) fps_cluster_kernel(const float *__restrict__ xyz, int N, int npoint,
@@ -107,8 +116,9 @@ __global__ void __launch_bounds__(FPSC_T, 1) fps_cluster_kernel(const float *__r
   cgr::cluster_group cluster = cgr::this_cluster();
   const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
   const int b = blockIdx.x / csize;
-  __shared__ FpsCand rec[2][FPSC_MAXC];    // written by every CTA of the cluster (slot = writer's rank)
+  __shared__ FpsCand rec[2][FPSC_MAXC];            // written by every CTA of the cluster (slot = writer's rank)
   __shared__ FpsCand wred[FPSC_T / 32];
+  __shared__ unsigned long long xbar[2];           // one arrival per CTA of the cluster and round (parity = round & 1)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const float *P = xyz + (size_t)b * N * 3;
   const int Ttot = csize * FPSC_T, gtid = crank * FPSC_T + tid;
@@ -121,12 +131,17 @@ __global__ void __launch_bounds__(FPSC_T, 1) fps_cluster_kernel(const float *__r
       pd[k] = 1e10f;                                        // pointnet2.py:65
     } else {
       px[k] = py[k] = pz[k] = 0.f;
-      pd[k] = -2.f;                                         // never selected, never updated (d >= 0 > -2 is false for `<`)
+      pd[k] = -2.f;                                         // never selected, never updated (d >= 0 < -2 is false)
     }
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&xbar[0])), "r"(csize));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fps_smem_u32(&xbar[1])), "r"(csize));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   int far = start_idx ? start_idx[b] : 0;                   // :66 (explicit instead of torch.randint)
   float cx = P[3 * far], cy = P[3 * far + 1], cz = P[3 * far + 2];
-  cluster.sync();                                           // every CTA's shared memory exists before remote writes
+  cluster.sync();                                           // barriers initialised in every CTA before remote arrivals
   for (int it = 0; it < npoint; it++) {
     if (crank == 0 && tid == 0) out_idx[(size_t)b * npoint + it] = far;   // :69
     if (it == npoint - 1) break;
@@ -138,48 +153,53 @@ __global__ void __launch_bounds__(FPSC_T, 1) fps_cluster_kernel(const float *__r
       if (d < pd[k]) pd[k] = d;                                          // :72-73
       if (pd[k] > bv) { bv = pd[k]; bi = gtid + k * Ttot; bx = px[k]; by = py[k]; bz = pz[k]; }   // k ascending = index ascending
     }
-    // warp: winner (value, index), then the winner's coordinates from its lane
-    float wv = bv;
-    int wi = bi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-      if (fps_better(wv, wi, ov, oi)) { wv = ov; wi = oi; }
-    }
-    const int src = __ffs(__ballot_sync(0xffffffffu, bi == wi)) - 1;
-    bx = __shfl_sync(0xffffffffu, bx, src); by = __shfl_sync(0xffffffffu, by, src); bz = __shfl_sync(0xffffffffu, bz, src);
-    if (lane == 0) { wred[wid].v = wv; wred[wid].i = wi; wred[wid].x = bx; wred[wid].y = by; wred[wid].z = bz; }
+    uint32_t wb;
+    int wi;
+    fps_warp_winner(bv, bi, wb, wi);
+    if (bi == wi) { wred[wid].v = bv; wred[wid].i = bi; wred[wid].x = bx; wred[wid].y = by; wred[wid].z = bz; }   // one lane
     __syncthreads();
     const int buf = it & 1;
     if (wid == 0) {
       FpsCand c;
-      c.v = -1.f; c.i = 0x7fffffff; c.x = c.y = c.z = 0.f;
+      c.v = -2.f; c.i = 0x7fffffff; c.x = c.y = c.z = 0.f;
       if (lane < FPSC_T / 32) c = wred[lane];
-      float v = c.v;
-      int i = c.i;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-        if (fps_better(v, i, ov, oi)) { v = ov; i = oi; }
-      }
-      const int s2 = __ffs(__ballot_sync(0xffffffffu, c.i == i && lane < FPSC_T / 32)) - 1;
-      const float x = __shfl_sync(0xffffffffu, c.x, s2), y = __shfl_sync(0xffffffffu, c.y, s2), z = __shfl_sync(0xffffffffu, c.z, s2);
-      if (lane < csize) {     // lane r delivers this CTA's candidate into CTA r's slot [crank]
+      uint32_t cb;
+      int ci;
+      fps_warp_winner(c.v, c.i, cb, ci);
+      const int src = __ffs(__ballot_sync(0xffffffffu, c.i == ci)) - 1;
+      const float v = __shfl_sync(0xffffffffu, c.v, src), x = __shfl_sync(0xffffffffu, c.x, src),
+                  y = __shfl_sync(0xffffffffu, c.y, src), z = __shfl_sync(0xffffffffu, c.z, src);
+      if (lane < csize) {     // lane r delivers this CTA's candidate into CTA r's slot [crank] and arrives on CTA r's barrier
         FpsCand *dst = cluster.map_shared_rank(&rec[buf][crank], lane);
-        dst->v = v; dst->x = x; dst->y = y; dst->z = z; dst->i = i;
+        dst->v = v; dst->x = x; dst->y = y; dst->z = z; dst->i = ci;
+        uint32_t rbar;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(fps_smem_u32(&xbar[buf])), "r"(lane));
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rbar) : "memory");
       }
     }
-    cluster.sync();           // release/acquire: all candidates of this round are visible in every CTA
-    float gv = -1.f;
+    {   // every thread waits for the csize arrivals of this round (acquire at cluster scope: the records are visible)
+      const uint32_t bar = fps_smem_u32(&xbar[buf]), parity = ((uint32_t)it >> 1) & 1u;
+      uint32_t ok;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      } while (!ok);
+    }
+    float gv = -2.f;
     int gi = 0x7fffffff;
     for (int r = 0; r < csize; r++) {
       const float ov = rec[buf][r].v;
       const int oi = rec[buf][r].i;
-      if (fps_better(gv, gi, ov, oi)) { gv = ov; gi = oi; cx = rec[buf][r].x; cy = rec[buf][r].y; cz = rec[buf][r].z; }
+      if (ov > gv || (ov == gv && oi < gi)) { gv = ov; gi = oi; cx = rec[buf][r].x; cy = rec[buf][r].y; cz = rec[buf][r].z; }
     }
     far = gi;                                               // :74 torch.max -> first max index
+    // wred is rewritten next round only after every thread passed this round's barrier wait; rec[buf] / xbar[buf] are
+    // reused two rounds later, after every CTA has completed round it + 1, i.e. after all of them finished reading here
   }
   cluster.sync();             // no CTA exits while a peer may still write into its shared memory
 }
@@ -309,9 +329,27 @@ extern "C" int cg_fps_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoin
     cudaGetLastError();
     csize_dev[ctx->device] = cs;
   }
-  const int csize = csize_dev[ctx->device];
+  // Cluster size: measured per-round cost ~ base(csize) + 0.025 us x points per thread, base = 0.70 / 0.83 / 1.0 / 1.45 us
+  // for 2 / 4 / 8 / 16 CTAs (the cross-CTA exchange is the floor: remote store + remote mbarrier arrive + acquire wait);
+  // pick the cheapest size whose points fit the 32-registers-per-thread budget.
+  int csize = csize_dev[ctx->device];
+  {
+    const int sizes[4] = {2, 4, 8, 16};
+    const double base[4] = {0.70, 0.83, 1.0, 1.45};
+    double best = 1e30;
+    for (int k = 0; k < 4; k++) {
+      if (sizes[k] > csize_dev[ctx->device]) break;
+      const long ppt = ((long)N + (long)sizes[k] * FPSC_T - 1) / ((long)sizes[k] * FPSC_T);
+      if (ppt > 32) continue;
+      const double cost = base[k] + 0.025 * (double)ppt;
+      if (cost < best) { best = cost; csize = sizes[k]; }
+    }
+  }
+#ifdef CG_EXPERIMENTS
+  if (getenv("CG_FPS_CLUSTER")) csize = atoi(getenv("CG_FPS_CLUSTER"));   // developer builds: cluster-size sweep
+#endif
   const long per_thread = ((long)N + (long)csize * FPSC_T - 1) / ((long)csize * FPSC_T);
-  CG_REQUIRE(ctx, per_thread <= 32, "fps: N too large (max 32 points per thread x 512 threads x cluster size)");
+  CG_REQUIRE(ctx, per_thread <= 32, "fps: N too large (max 32 points per thread x 256 threads x cluster size)");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(B * csize));
   cfg.blockDim = dim3(FPSC_T);

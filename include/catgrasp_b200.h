@@ -284,8 +284,8 @@ int cg_index_points_dev(cg_ctx *ctx, const float *points, const int32_t *idx,
                         int B, int N, int C, int S, float *out);
 /* pointnet2.py:54-75  farthest_point_sample with explicit start indices.
  * cg_fps_dev: one thread-block cluster per cloud, points + running distances in
- * registers, one distributed-shared-memory exchange per round (N <= 131072 /
- * 262144 points for cluster size 8 / 16).  cg_fps_single_cta_dev: the round-1
+ * registers, one distributed-shared-memory exchange per round (N <= 65536 /
+ * 131072 points for cluster size 8 / 16).  cg_fps_single_cta_dev: the round-1
  * one-CTA kernel (N <= 56320), kept for comparison.                           */
 int cg_fps_dev(cg_ctx *ctx, const float *xyz, int B, int N, int npoint,
                const int32_t *start_idx, int32_t *out_idx);
