@@ -14,12 +14,13 @@
 // max |dprob| 4e-6, max |dlogit| 3e-5 against the fp32 oracle (tolerance 1e-4).  X3 values above the fp16 range are
 // clamped to 65504 AND reported through cg_trunk_args::ovf_flag so the host can fall back to engine 1.
 //
-// Warp roles (480 threads, 1 CTA / SM):
+// Warp roles (608 threads, 1 CTA / SM):
 //   warps 0-7   front : thread = (point, channel half): input build + 6->64 FMA layer, L1 / L2 epilogues
-//   warps 8-11  max   : L3 epilogue: 16x256b TMEM loads + FMNMX3 / shuffle column max over the tile's 128 points
-//   warp  12    W3 producer: streams the fp16 W3 image through a 3 x 32 KB ring with cp.async.bulk (UBLKCP)
-//   warp  13    UMMA issuer (one elected lane)
-//   warp  14    aux: per-candidate constants (float64 pose inverse, T3, and the per-candidate 64x64 feature transform
+//   warps 8-15  max   : L3 epilogue: 16x256b TMEM loads + FMNMX3 / shuffle column max over the tile's 128 points;
+//                       warp = (TMEM lane quarter, column half) -- one warp alone reads TMEM at only ~31 B/cycle
+//   warp  16    W3 producer: streams the fp16 W3 image through a 3 x 32 KB ring with cp.async.bulk (UBLKCP)
+//   warp  17    UMMA issuer (one elected lane)
+//   warp  18    aux: per-candidate constants (float64 pose inverse, T3, and the per-candidate 64x64 feature transform
 //               of pointnet2.py:257 converted into a UMMA B-operand image), double-buffered one candidate ahead
 // All hand-overs are mbarriers; the front layers of tile t+1 run in the shadow of tile t's L3 stream.
 #include <cuda_bf16.h>
@@ -263,9 +264,11 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     }
   } else if (warp == MMA_WARP) {
     // ======================= UMMA issuer: the warp stays converged, one elected lane issues =======================
-    // (Measured: tcgen05.mma issue is synchronous with the tensor pipe -- ~75 cycles per 128x128x16 UMMA in the issuing
-    // thread -- so waits in this thread are pipe bubbles.  A second issuer warp for the L1/L2 layers was tried and was
-    // SLOWER (768 vs 850 TFLOP/s): the front warps' chain then gates the L3 stream through x3 instead of x1/x2.)
+    // Measured: tcgen05.mma issue is nearly synchronous with the tensor pipe (~75 cycles per
+    // 128x128x16 UMMA in the issuing thread) and the pipe executes in issue order, so where the L1 / L2 UMMAs of the next
+    // tile are placed inside the L3 stream decides how long the front warps' chain is.  Fixed slots (L1 after chunk 1, L2
+    // after chunk 3) measured best: 826-850 TFLOP/s; later slots (chunks 2 / 4) 767; run-time placement by non-blocking
+    // probes 789; a second issuer warp for L1 / L2 768.
     const uint32_t wb = smem_u32(&S.w_bar);
     if (elect_one()) {
       mbar_expect_tx(wb, IMG_W2 + (a.stage1_mode == 1 ? IMG_W1 : 0u));
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     // ======================= max warps: L3 epilogue =======================
     // D3[pt][ch]: TMEM lanes = points.  Each warp owns the 32 lanes of its quarter; a 16x256b load hands every
     // thread 4 points x 16 columns, so the column max is 2 FMNMX3/FMNMX per value + a 3-step exchange (14 shuffles
-    // for 64 columns); the four warps meet in the shared running max of the candidate.
+    // for 64 columns); the eight warps (lane quarter x column half) meet in the shared running max of the candidate.
     const int q = warp & 3, hsel = (warp - NFRONT) >> 2;   // TMEM lane quarter, column half of every 128-channel chunk
     const uint32_t lane_lo = (uint32_t)(q * 32) << 16, lane_hi = (uint32_t)(q * 32 + 16) << 16;
     const int mt = tid - NFT;   // 0..255
