@@ -39,9 +39,10 @@ using namespace cg_ptx;
 constexpr int NFRONT = 8;
 constexpr int NMAXW = 8;
 constexpr int PROD_WARP = NFRONT + NMAXW;   // 16
-constexpr int MMA_WARP = PROD_WARP + 1;     // 17
-constexpr int AUX_WARP = MMA_WARP + 1;      // 18
-constexpr int NTP = (AUX_WARP + 1) * 32;    // 608 threads
+constexpr int MMA_WARP = PROD_WARP + 1;     // 17: issuer A (even L3 chunks)
+constexpr int MMAB_WARP = MMA_WARP + 1;     // 18: issuer B (odd L3 chunks + the L1 / L2 UMMAs of the next tile)
+constexpr int AUX_WARP = MMAB_WARP + 1;     // 19
+constexpr int NTP = (AUX_WARP + 1) * 32;    // 640 threads
 constexpr int NFT = NFRONT * 32;            // 256 front threads
 constexpr uint32_t PIECE = 16384;           // [128 rows x 64 x 16-bit] one swizzled K-block
 constexpr uint32_t XA_OFF = 0;              // [hi|lo] 32 KB: X1 (L1 input), then X2 (L2 input) of the same tile
@@ -77,6 +78,7 @@ struct MiscP {
   unsigned long long x1_bar, x2_bar, x3_bar;   // front -> MMA : XA holds X1 / XA holds X2 / X3 written to TMEM
   unsigned long long l1_bar, l2_bar;    // MMA -> front    : D1 / D2 complete
   unsigned long long w_bar;             // resident W2 (+ shared W1) landed
+  unsigned long long a_done[2];         // issuer A -> issuer B: A's L3 UMMAs of tile it (parity it & 1) completed
   unsigned long long cc_full[2], cc_free[2];   // aux <-> front : per-candidate constants
   unsigned long long w1_full[2], w1_free[2];   // aux <-> MMA   : per-candidate L1 operand (stage1_mode 2)
   uint32_t tmem_base;
@@ -190,6 +192,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     mbar_init(smem_u32(&S.l1_bar), 1);
     mbar_init(smem_u32(&S.l2_bar), 1);
     mbar_init(smem_u32(&S.w_bar), 1);
+    mbar_init(smem_u32(&S.a_done[0]), 1);
+    mbar_init(smem_u32(&S.a_done[1]), 1);
     mbar_init_fence();
   }
   if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS);
@@ -262,29 +266,21 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         if (lane == 0) mbar_arrive(smem_u32(&S.w1_full[slot]));
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ======================= UMMA issuer: the warp stays converged, one elected lane issues =======================
+  } else if (warp == MMA_WARP || warp == MMAB_WARP) {
+    // ======================= UMMA issuers A / B: the warps stay converged, one elected lane issues =======================
     // Measured: tcgen05.mma issue is nearly synchronous with the tensor pipe (~75 cycles per
-    // 128x128x16 UMMA in the issuing thread) and the pipe executes in issue order, so where the L1 / L2 UMMAs of the next
-    // tile are placed inside the L3 stream decides how long the front warps' chain is.  Fixed slots (L1 after chunk 1, L2
-    // after chunk 3) measured best: 826-850 TFLOP/s; later slots (chunks 2 / 4) 767; run-time placement by non-blocking
-    // probes 789; a second issuer warp for L1 / L2 768.
+    // 128x128x16 UMMA in the issuing thread) and each chunk costs the issuer another ~400 cycles of waits / fences / commits
+    // during which a single issuer leaves the pipe empty.  Two issuers alternate over the chunks (A: even chunks ->
+    // accumulator 0, B: odd chunks -> accumulator 1): while one is blocked issuing, the other does its hand-overs.  B also
+    // issues the L1 / L2 UMMAs of the next tile at the fixed slots that measured best with one issuer (after chunks 1 and 3;
+    // later slots 767 vs 826-850 TFLOP/s, run-time placement by probes 789, a separate issuer for L1 / L2 only 768).
+    const bool isB = warp == MMAB_WARP;
     const uint32_t wb = smem_u32(&S.w_bar);
-    if (elect_one()) {
-      mbar_expect_tx(wb, IMG_W2 + (a.stage1_mode == 1 ? IMG_W1 : 0u));
-      bulk_g2s(w2_s, img + IMG_W3, PIECE, wb);
-      bulk_g2s(w2_s + PIECE, img + IMG_W3 + PIECE, PIECE, wb);
-      if (a.stage1_mode == 1) bulk_g2s(w1_s, img + IMG_W3 + IMG_W2, IMG_W1, wb);
-    }
-    __syncwarp();
-    mbar_wait(wb, 0u);
     const uint32_t l1b = smem_u32(&S.l1_bar), l2b = smem_u32(&S.l2_bar);
     uint32_t ph_x1 = 0u, ph_x2 = 0u;
-    int rslot = 0;
-    uint32_t rph = 0u;
     int b_prev = -1;
     long long t_all = clock64(), t_x3 = 0, t_ring = 0, t_accf = 0, t_x12 = 0, tw;
-    // front layers (L1, L2) of local tile `itn`
+    // front layers (L1, L2) of local tile `itn` (issuer B only)
     auto issue_l1 = [&](int itn) {
       int b, tile;
       locate(itn, b, tile);
@@ -315,20 +311,37 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       }
       __syncwarp();
     };
-    if (has_l1) issue_l1(0);
-    issue_l2(0);
+    // D1 / D2 of tile itn land in the activation block XB(itn) = XB(itn - 2), whose X3 issuer A's chunks of tile itn - 2
+    // read: they must have completed (B's own chunks are ordered before by issue order)
+    auto guard_xb = [&](int itn) {
+      if (itn >= 2) mbar_wait(smem_u32(&S.a_done[itn & 1]), (((uint32_t)itn >> 1) - 1u) & 1u);
+    };
+    if (isB) {
+      if (elect_one()) {
+        mbar_expect_tx(wb, IMG_W2 + (a.stage1_mode == 1 ? IMG_W1 : 0u));
+        bulk_g2s(w2_s, img + IMG_W3, PIECE, wb);
+        bulk_g2s(w2_s + PIECE, img + IMG_W3 + PIECE, PIECE, wb);
+        if (a.stage1_mode == 1) bulk_g2s(w1_s, img + IMG_W3 + IMG_W2, IMG_W1, wb);
+      }
+      __syncwarp();
+      mbar_wait(wb, 0u);
+      if (has_l1) issue_l1(0);
+      issue_l2(0);
+    }
     constexpr uint32_t id3 = umma_idesc(128, 128, 0u, 0u);   // f16 x f16 -> f32
+    const int buf = isB ? 1 : 0;
     for (int it = 0; it < T; it++) {
       tw = clock64();
       mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
       t_x3 += clock64() - tw;
-      const bool tr = (it == T / 2) && lane == 0;
+      const bool tr = (it == T / 2) && lane == 0 && !isB;
       CG_TRACE_AT(tr, 0);
       const bool has_next = it + 1 < T;
       const uint32_t x3c = tmem_base + xb_col(it);
-      for (int c = 0; c < NCHUNK; c++) {
-        const int buf = c & 1;
+      for (int c = buf; c < NCHUNK; c += 2) {
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
+        const uint32_t gidx = (uint32_t)it * NCHUNK + (uint32_t)c;     // chunk number in the W3 stream
+        const uint32_t rslot = gidx % NPAIR, rph = (gidx / NPAIR) & 1u;
         if (a.dbg) {   // instrumented run: time the two waits separately
           tw = clock64();
           if (use >= 1u) mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         CG_TRACE_AT(tr, 1 + 2 * c);
         const uint32_t d = tmem_base + (uint32_t)buf * 128u;
         if (elect_one()) {
-          const uint32_t w_s = ring_s + (uint32_t)rslot * 2 * PIECE;
+          const uint32_t w_s = ring_s + rslot * 2 * PIECE;
 #pragma unroll
           for (int i = 0; i < (CG_EXP(a, 16) ? 0 : 2); i++) {
 #pragma unroll
@@ -357,30 +370,29 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           }
           umma_commit(smem_u32(&S.free_bar[rslot]));
           umma_commit(smem_u32(&S.acc_bar[buf]));
+          if (!isB && c == NCHUNK - 2) umma_commit(smem_u32(&S.a_done[it & 1]));
         }
         __syncwarp();
         CG_TRACE_AT(tr, 2 + 2 * c);
-        if (++rslot == NPAIR) { rslot = 0; rph ^= 1u; }
-        // front layers of the NEXT tile run in the shadow of this tile's L3 stream
-        if (has_next && c == (CG_EXP(a, 32) ? 2 : 1) && has_l1) {
+        // front layers of the NEXT tile run in the shadow of this tile's L3 stream (issuer B)
+        if (isB && has_next && c == 1 && has_l1) {
           tw = clock64();
-          CG_TRACE_AT(tr, 17);
+          guard_xb(it + 1);
           issue_l1(it + 1);
-          CG_TRACE_AT(tr, 18);
           t_x12 += clock64() - tw;
         }
-        if (has_next && c == (has_l1 ? (CG_EXP(a, 32) ? 4 : 3) : (CG_EXP(a, 32) ? 2 : 1))) {
+        if (isB && has_next && c == (has_l1 ? 3 : 1)) {
           tw = clock64();
-          CG_TRACE_AT(tr, 19);
+          if (!has_l1) guard_xb(it + 1);
           issue_l2(it + 1);
-          CG_TRACE_AT(tr, 20);
           t_x12 += clock64() - tw;
         }
       }
     }
     if (a.dbg && lane == 0) {
       unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
-      dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_ring; dd[3] = t_accf; dd[4] = t_x12; dd[5] = T;
+      if (!isB) { dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_ring; dd[3] = t_accf; dd[5] = T; }
+      else dd[4] = t_x12;
     }
   } else if (warp >= NFRONT) {
     // ======================= max warps: L3 epilogue =======================
