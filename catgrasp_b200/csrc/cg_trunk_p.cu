@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const int p = tid & 127, half = tid >> 7;
     const int q = warp & 3;                         // TMEM lane quadrant of this warp
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    unsigned ovf = 0u;
+    float vmax = 0.f;   // largest 128->1024 input seen by this thread (post-ReLU, >= 0): reported if beyond the fp16 range
     long long f_all = clock64(), f_l2 = 0, f_l1 = 0, fw;
     // raw input row of this thread's point for the tile being prepared (prefetched one tile ahead so that the
     // dependent global loads ids -> cloud row are off the critical path between two tiles)
@@ -474,10 +474,15 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     float rv[6];
     int id_next = 0;   // scene-point index of this thread's point two tiles ahead (the ids load is one more tile ahead
                        // of the dependent cloud-row loads, so neither ever stalls the front pipeline)
+    // (candidate, tile) cursors: the lambdas below are called with consecutive local tile indices, so the flattened index
+    // is decomposed once and then advanced (an integer division per call and thread showed up in the front warps' time)
+    int pid_b, pid_tile, l0_b, l0_tile;
+    locate(0, pid_b, pid_tile);
+    l0_b = pid_b; l0_tile = pid_tile;
     auto prefetch_id = [&](int it) {
       if (a.in.x_direct || it >= T) return;
-      int b, tile;
-      locate(it, b, tile);
+      const int b = pid_b, tile = pid_tile;
+      if (++pid_tile == ntiles) { pid_tile = 0; pid_b++; }
       int n = tile * TP + p;
       if (n >= N) n = N - 1;   // duplicate a valid point: cannot change a max
       id_next = a.in.ids ? __ldg(a.in.ids + (size_t)b * N + n) : n;
@@ -503,13 +508,12 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     int b_l0 = -1;   // candidate of the previous layer0 call
     // 6 -> 64 (+bias, ReLU) of the prefetched row -> this thread's 32-channel slice of the XA tile
     auto layer0 = [&](int it) {
-      int b, tile;
-      locate(it, b, tile);
+      const int b = l0_b;
+      const bool last_of_cand = (it == T - 1) || (l0_tile == ntiles - 1);
+      if (++l0_tile == ntiles) { l0_tile = 0; l0_b++; }
       const int lc = b - b_first, slot = lc & 1;
       if (b != b_l0) mbar_wait(smem_u32(&S.cc_full[slot]), ((uint32_t)lc >> 1) & 1u);
       b_l0 = b;
-      int bn, tn;
-      const bool last_of_cand = (it == T - 1) || (locate(it + 1, bn, tn), bn != b);
       const CandConst &C = S.cc[slot];
       float v[6];
       if (a.in.x_direct) {
@@ -649,9 +653,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         for (int j = 0; j < 16; j++) {
           const float a0 = fmaxf(v[2 * j] + S.bias2[half * 64 + j32 * 32 + 2 * j], 0.f);
           const float a1 = fmaxf(v[2 * j + 1] + S.bias2[half * 64 + j32 * 32 + 2 * j + 1], 0.f);
-          ovf |= (a0 > 65504.f) | (a1 > 65504.f);
-          const __half2 hh = __floats2half2_rn(fminf(a0, 65504.f), fminf(a1, 65504.f));
-          ph[j32 * 16 + j] = *reinterpret_cast<const uint32_t *>(&hh);
+          vmax = fmax3(vmax, a0, a1);
+          // F2FP.SATFINITE: values beyond the fp16 range saturate to 65504 instead of becoming inf (a0 -> low half)
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ph[j32 * 16 + j]) : "f"(a1), "f"(a0));
         }
       }
       // word j of this thread = channels (half*64 + 2j, +1) of its point = packed K column half*32 + j;
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       // D. L1 epilogue of the next tile
       if (has_next && has_l1) l1_epilogue(it + 1);
     }
-    if (ovf && a.ovf_flag) atomicOr(a.ovf_flag, 1u);
+    if (vmax > 65504.f && a.ovf_flag) atomicOr(a.ovf_flag, 1u);
     if (a.dbg && tid == 0) {
       unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
       dd[8] = clock64() - f_all; dd[9] = f_l2; dd[10] = f_l1;
