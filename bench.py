@@ -232,7 +232,7 @@ def pick_torch_threads(sd_cls, n_pts):
 
 def cpu_reference_pass(job, args, n_cand, sd_cls, sd_seg, mean, std, gripper, with_nunocs=True):
     """The reference's CPU path for n_cand candidates: per-candidate numpy transform loop + PointNetCls in
-    micro-batches of 200 (predicter.py:67-94), C collision oracle with OpenMP on all cores, and (optionally) NUNOCS
+    micro-batches of 200 (predicter.py:67-94), C collision oracle with OpenMP, and (optionally) NUNOCS
     forwards (the first one is a warm-up, the second is the one timed)."""
     from oracle import filter_ref
     from oracle.transforms_ref import nunocs_predict, predict_batch
@@ -243,8 +243,12 @@ def cpu_reference_pass(job, args, n_cand, sd_cls, sd_seg, mean, std, gripper, wi
     predict_batch(sd_cls, cfg, data, job["poses"][:n_cand])
     t1 = time.perf_counter()
     eye = np.eye(4)
+    # The C collision oracle runs on the same OpenMP runtime as torch.  With one OpenMP team of all 128 host cores every
+    # later torch region of the process slowed down 4-30x (round 1 measured its NUNOCS forward right after such a region:
+    # 5 s instead of ~0.2 s); the collision share is ~0.02 s per step either way, so it uses torch's thread count.
+    import torch
     filter_ref.filter_ref(job["poses"][:n_cand], [eye], eye, eye, gripper["gripper_in_grasp"], True, True, 0, gripper["open"],
-                          job["open_pts"], gripper["enclosed"], job["bg_pts"], nthreads=os.cpu_count())
+                          job["open_pts"], gripper["enclosed"], job["bg_pts"], nthreads=torch.get_num_threads())
     t2 = time.perf_counter()
     nun = 0.0
     if with_nunocs:
@@ -293,7 +297,7 @@ def run_reference(args):
     cores = os.cpu_count()
     sample = (f"{n} of {per_scene} candidates per step on a {job['M']}-pt scene (net {tot_s['net_s'] / args.steps:.2f} s, collision "
               f"{tot_s['collision_s'] / args.steps:.3f} s per step); warm NUNOCS forward ({nun_s:.2f} s) amortised 1 per {per_scene} "
-              f"candidates; torch threads {th} (picked by a sweep), OpenMP collision threads {cores}; PORT of the reference "
+              f"candidates; torch threads {th} (picked by a sweep), OpenMP collision threads {th}; PORT of the reference "
               f"(oracle/), not its own binaries; context: the reference's pointnet2.PointNetCls itself ran 134 cand/s on 8 cores "
               f"in the survey container (BASELINE.md section 2)")
     line = {"impl": "reference", "metric": "candidate grasps scored/sec", "value": v, "unit": "candidates/s",
@@ -615,7 +619,7 @@ def main():
         line["cpu_baseline"] = {"value": cpu_rate(r, n, per_scene), "unit": "candidates/s", "cores": os.cpu_count(),
                                 "kind": "port", "sample": f"{n} of {per_scene} candidates (net {r['net_s']:.2f}s, collision "
                                 f"{r['collision_s']:.2f}s) + 1 warm NUNOCS forward ({r['nunocs_s']:.2f}s, amortised 1 per {per_scene} "
-                                f"candidates); torch threads {th} (sweep), OpenMP {os.cpu_count()}; oracle PORT of the reference; "
+                                f"candidates); torch threads {th} (sweep), OpenMP collision threads {th}; oracle PORT of the reference; "
                                 f"the reference's own PointNetCls ran 134 cand/s on 8 cores in the survey container"}
     print(json.dumps(line))
     if world > 1:
