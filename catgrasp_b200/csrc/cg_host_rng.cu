@@ -99,23 +99,35 @@ static void shuffle_one(Mt &g, int64_t M, int32_t n_pts, int32_t *p, int32_t *ou
 }
 
 // Advances g exactly as shuffle_one would, without touching a permutation (which words are accepted does not depend
-// on the permutation): the sequential part of the multi-threaded draw.
+// on the permutation): the sequential part of the multi-threaded draw.  The tempering + masking of a block of raw words
+// has no loop-carried dependency (the compiler vectorises it); only the accept scan `i -= (j <= i)` is serial, and the mask
+// is constant while i stays above mask >> 1.
 static void shuffle_skip(Mt &g, int64_t M) {
   uint32_t mask = mask_of((uint32_t)(M - 1));
   uint32_t i = (uint32_t)(M - 1);
+  uint32_t tmp[MT_N];
   while (i >= 1) {
     if (g.pos == MT_N) g.refill();
     const int avail = MT_N - g.pos;
     const uint32_t *kp = g.key + g.pos;
-    int k = 0;
-    for (; k < avail && i >= 1; k++) {
+    for (int k = 0; k < avail; k++) {
       uint32_t y = kp[k];
       y ^= (y >> 11);
       y ^= (y << 7) & 0x9d2c5680u;
       y ^= (y << 15) & 0xefc60000u;
       y ^= (y >> 18);
-      i -= ((y & mask) <= i) ? 1u : 0u;
-      if ((mask >> 1) >= i) mask >>= 1;
+      tmp[k] = y;
+    }
+    int k = 0;
+    while (k < avail && i >= 1) {
+      // segment with a constant mask: i in (mask >> 1, mask]
+      const uint32_t lim = mask >> 1;
+      const uint32_t m = mask;
+      while (k < avail && i > lim) {
+        i -= ((tmp[k] & m) <= i) ? 1u : 0u;
+        k++;
+      }
+      if (i <= lim) mask >>= 1;   // i crossed below the next power of two (i >= 1 keeps mask >= 1)
     }
     g.pos += k;
   }
