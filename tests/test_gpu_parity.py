@@ -703,7 +703,8 @@ def test_predict_batch_vs_reference_run(cuda, golden_dir, tmp_path, engine):
     adir = write_artifacts(str(tmp_path / "artifacts-47"), "cls", n_pts=1024, seed=int(g["artifact_seed"]),
                            logit_gain=float(g["logit_gain"]))
     gp = GraspPredicter("nut", artifact_dir=adir)
-    _lib.Context.get(0).set_engine(engine)
+    assert gp.engine in (1, 3) and gp.engine_probe["max_abs_dprob"] < PROB_TOL      # load-time gate ran on this checkpoint
+    gp.engine = engine                                                              # ... and can be overridden
     try:
         for tag in ("big", "small"):
             data = {"cloud_xyz": g[f"{tag}_cloud_xyz"].astype(np.float64), "cloud_normal": g[f"{tag}_cloud_normal"].astype(np.float64)}
