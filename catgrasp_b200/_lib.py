@@ -58,6 +58,7 @@ SIGNATURES = {
     "cg_graspq_forward_dev": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "cg_host_legacy_choice": (_i, [_vp, C.POINTER(C.c_int32), C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32]),
     "cg_host_legacy_skip": (_i, [_vp, C.POINTER(C.c_int32), C.c_int64, C.c_int32, C.c_int32]),
+    "cg_host_rng_isa": (_i, [_i]),
     "cg_draw_ids_dev": (_i, [_vp, _i, _i, _i, C.c_uint64, C.c_int64, _vp]),
     "cg_mlp_create": (_i, [_vp, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
     "cg_mlp_destroy": (None, [_vp]),

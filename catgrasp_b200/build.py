@@ -16,8 +16,11 @@ if os.environ.get("CG_BUILD_EXPERIMENTS") == "1":   # developer builds only: CG_
     NVCC_FLAGS.append("-DCG_EXPERIMENTS")
 
 
+CXX_FLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread"]   # host-only sources (*.cpp): straight through g++
+
+
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
 def _stale():
@@ -38,16 +41,19 @@ def build(force=False, verbose=False):
     obj_dir = os.path.join(LIB_DIR, "obj")
     os.makedirs(obj_dir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(obj_dir, os.path.splitext(os.path.basename(src))[0] + ".o")
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        if src.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++")] + CXX_FLAGS + ["-c", src, "-o", obj]
+        else:
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
             print(out)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}")
+            raise RuntimeError(f"compiler failed on {src}")
     subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread",
                            "-o", LIB] + objs)
     return LIB

@@ -119,7 +119,7 @@ class GraspPredicter:
         self.model = PointNetCls(sd, device=device)
         assert self.model.n_out == n_out, f"checkpoint has {self.model.n_out} classes, config says {n_out}"
         self.subsample = "host"       # "host": the reference's numpy draw, bit for bit; "device": counter-based draw on the GPU
-        self.chunk = 512              # candidates per pipeline stage (host draw of chunk k+1 overlaps the GPU on chunk k)
+        self.chunk = 1024             # candidates per pipeline stage (host draw of chunk k+1 overlaps the GPU on chunk k)
         self._pin = None
         self.engine = self._pick_engine() if engine == "auto" else int(engine)
 

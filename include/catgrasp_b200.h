@@ -126,8 +126,11 @@ int cg_graspq_forward_dev(cg_net *net,
  * MT19937 state of np.random.get_state() (fields 1 and 2); both are advanced
  * exactly as numpy would advance them, so np.random.set_state() afterwards
  * leaves the host program on the reference's random stream.  The stream walk
- * is sequential; the permutations are replayed on `nthreads` host threads
- * (<= 0: one per core, at most 32).  out: (count, n_pts) int32.
+ * is sequential (AVX-512 / AVX2 / scalar, picked at load time); the
+ * permutations are replayed on `nthreads` host threads (<= 0: one per core,
+ * at most 12).  out: (count, n_pts) int32.
+ * cg_host_rng_isa(level) caps the instruction set (0 scalar, 1 AVX2, 2 AVX-512,
+ * -1 best available) and returns the level in use -- a test hook.
  *
  * cg_draw_ids_dev (opt-in, NOT the reference's numbers): a counter-based draw
  * on the device with the same distribution -- n_pts distinct uniform indices
@@ -139,6 +142,7 @@ int cg_host_legacy_choice(uint32_t *key, int32_t *pos, int64_t M, int32_t n_pts,
                           int32_t count, int32_t *out, int32_t nthreads);
 /* advance the generator over `count` candidates without producing their indices (sharded scoring) */
 int cg_host_legacy_skip(uint32_t *key, int32_t *pos, int64_t M, int32_t n_pts, int32_t count);
+int cg_host_rng_isa(int level);
 int cg_draw_ids_dev(cg_ctx *ctx, int M, int n_pts, int count, uint64_t seed,
                     int64_t first_candidate, int32_t *out_ids);
 

@@ -241,12 +241,14 @@ def test_host_pose_composition_is_bit_identical_to_the_oracle():
 # ------------------------------------------------------------------ the subset draw (host half of GraspDataset.transform)
 @pytest.mark.parametrize("M,n_pts,count", [(20000, 1024, 24), (3000, 1024, 40), (2048, 2048, 9), (1024, 1024, 12),
                                            (700, 1024, 12), (1, 5, 3), (2, 2, 4), (5, 8, 6), (1025, 1024, 7)])
-@pytest.mark.parametrize("nthreads", [1, 0])
-def test_c_legacy_choice_equals_numpy(M, n_pts, count, nthreads):
+@pytest.mark.parametrize("nthreads,isa", [(1, -1), (0, -1), (3, 0), (3, 1)])
+def test_c_legacy_choice_equals_numpy(M, n_pts, count, nthreads, isa):
     """cg_host_legacy_choice continues numpy's GLOBAL MT19937 stream exactly like the reference's per-candidate
     ``np.random.choice(np.arange(M), size=n_pts, replace=M < n_pts)`` (dataset_grasp.py:72-73): same indices, and the
     generator is left in the same state (next uniform AND next gaussian draws agree), single- and multi-threaded."""
+    from catgrasp_b200 import _lib
     from catgrasp_b200.predicter import _LegacyDraw, draw_subsample_ids_numpy
+    _lib.load().cg_host_rng_isa(isa)        # -1: best of AVX-512 / AVX2 / scalar on this host; 0 / 1: capped
     np.random.seed(123)
     np.random.rand(3)
     np.random.randn(1)                      # leaves a cached gaussian in the state tuple
@@ -259,9 +261,31 @@ def test_c_legacy_choice_equals_numpy(M, n_pts, count, nthreads):
     a = d.draw(M, n_pts, count // 2, nthreads=nthreads)          # two chunks: the pipelined predict_batch does this
     b = d.draw(M, n_pts, count - count // 2, nthreads=nthreads)
     d.commit()
+    _lib.load().cg_host_rng_isa(-1)
     got_next = (np.random.rand(4), np.random.randn(3))
     assert np.array_equal(np.concatenate([a, b]), ref)
     assert np.array_equal(ref_next[0], got_next[0]) and np.array_equal(ref_next[1], got_next[1])
+
+
+@pytest.mark.parametrize("isa", [0, 1, 2])
+def test_c_legacy_skip_equals_draw(isa):
+    """cg_host_legacy_skip (the stream walk of a sharded call) leaves the generator exactly where drawing leaves it, on
+    every instruction-set level, including sizes around the power-of-two mask changes."""
+    from catgrasp_b200 import _lib
+    from catgrasp_b200.predicter import _LegacyDraw
+    lib = _lib.load()
+    try:
+        lib.cg_host_rng_isa(isa)
+        for M, n_pts, count in ((20000, 1024, 9), (16384, 1024, 5), (16385, 1024, 5), (4097, 4096, 3), (33, 16, 50), (700, 1024, 7)):
+            np.random.seed(5 + M)
+            a = _LegacyDraw()
+            a.draw(M, n_pts, count, nthreads=1)
+            np.random.seed(5 + M)
+            b = _LegacyDraw()
+            b.skip(M, n_pts, count)
+            assert np.array_equal(a.key, b.key) and a.pos.value == b.pos.value, (M, n_pts)
+    finally:
+        lib.cg_host_rng_isa(-1)
 
 
 def test_draw_subsample_ids_wrapper_consumes_like_reference():
