@@ -63,7 +63,7 @@ struct CandConst {
 };
 
 struct MiscP {
-  uint32_t gmax_s[2][1024];   // running max per channel (order-preserving keys), buffer = local candidate index & 1
+  float2 sacc[NCHUNK][NMAXW][32];   // running max of the current candidate: a private slot per (chunk, max warp, lane)
   float w0[6 * 64];
   float bias0[64];
   float bias1[64];
@@ -83,6 +83,9 @@ struct MiscP {
   unsigned long long w1_full[2], w1_free[2];   // aux <-> MMA   : per-candidate L1 operand (stage1_mode 2)
   uint32_t tmem_base;
 };
+
+#define SBAR(field) (misc_s + (uint32_t)offsetof(MiscP, field))
+#define SBARI(field, i) (misc_s + (uint32_t)offsetof(MiscP, field) + (uint32_t)(i) * 8u)
 
 #ifdef CG_EXPERIMENTS
 #define CG_EXP(a, bit) (((a).exp_flags & (bit)) != 0)
@@ -149,6 +152,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   unsigned char *xa = smem + XA_OFF, *w1 = smem + W1_OFF;
   MiscP &S = *reinterpret_cast<MiscP *>(smem + MISC_OFF);
+  // shared-space address of the barrier block, converted once: every barrier operand below is misc_s + a constant
+  // (a generic-to-shared conversion per use showed up with 5-7 % of the stall samples)
+  const uint32_t misc_s = smem_u32(smem) + MISC_OFF;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N;
   // contiguous range of flattened (candidate, tile) work items of this CTA
@@ -162,7 +168,6 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
   const bool percand_w1 = a.stage1_mode == 2;
 
   // ---- one-time setup -------------------------------------------------------------------------------------
-  for (int i = tid; i < 2048; i += NTP) (&S.gmax_s[0][0])[i] = 0u;
   for (int i = tid; i < 6 * 64; i += NTP) S.w0[i] = a.l0.Wt[i];
   if (tid < 64) {
     S.bias0[tid] = a.l0.b[tid];
@@ -175,28 +180,28 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
   }
   if (tid == 0) {
     for (int i = 0; i < NPAIR; i++) {
-      mbar_init(smem_u32(&S.full_bar[i]), 1);
-      mbar_init(smem_u32(&S.free_bar[i]), 1);
+      mbar_init(SBARI(full_bar, i), 1);
+      mbar_init(SBARI(free_bar, i), 1);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(smem_u32(&S.acc_bar[i]), 1);
-      mbar_init(smem_u32(&S.accfree_bar[i]), NMAXW);
-      mbar_init(smem_u32(&S.cc_full[i]), 1);
-      mbar_init(smem_u32(&S.cc_free[i]), 1);
-      mbar_init(smem_u32(&S.w1_full[i]), 1);
-      mbar_init(smem_u32(&S.w1_free[i]), 1);
+      mbar_init(SBARI(acc_bar, i), 1);
+      mbar_init(SBARI(accfree_bar, i), NMAXW);
+      mbar_init(SBARI(cc_full, i), 1);
+      mbar_init(SBARI(cc_free, i), 1);
+      mbar_init(SBARI(w1_full, i), 1);
+      mbar_init(SBARI(w1_free, i), 1);
     }
-    mbar_init(smem_u32(&S.x1_bar), 1);
-    mbar_init(smem_u32(&S.x2_bar), 1);
-    mbar_init(smem_u32(&S.x3_bar), 1);
-    mbar_init(smem_u32(&S.l1_bar), 1);
-    mbar_init(smem_u32(&S.l2_bar), 1);
-    mbar_init(smem_u32(&S.w_bar), 1);
-    mbar_init(smem_u32(&S.a_done[0]), 1);
-    mbar_init(smem_u32(&S.a_done[1]), 1);
+    mbar_init(SBAR(x1_bar), 1);
+    mbar_init(SBAR(x2_bar), 1);
+    mbar_init(SBAR(x3_bar), 1);
+    mbar_init(SBAR(l1_bar), 1);
+    mbar_init(SBAR(l2_bar), 1);
+    mbar_init(SBAR(w_bar), 1);
+    mbar_init(SBARI(a_done, 0), 1);
+    mbar_init(SBARI(a_done, 1), 1);
     mbar_init_fence();
   }
-  if (warp == 0) tmem_alloc(smem_u32(&S.tmem_base), TMEM_COLS);
+  if (warp == 0) tmem_alloc(SBAR(tmem_base), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -219,9 +224,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     uint32_t ph = 1u;   // a fresh barrier passes a wait on parity 1: the first round does not block
     int chunk = 0;   // every tile starts with chunk 0
     for (int gp = 0; gp < total; gp++) {
-      mbar_wait(smem_u32(&S.free_bar[slot]), ph);
+      mbar_wait(SBARI(free_bar, slot), ph);
       if (elect_one()) {
-        const uint32_t fb = smem_u32(&S.full_bar[slot]);
+        const uint32_t fb = SBARI(full_bar, slot);
         if (CG_EXP(a, 1) && gp >= NPAIR) {
           mbar_arrive(fb);   // timing experiment: no W3 traffic after the first round
         } else {
@@ -241,14 +246,14 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     for (int b = b_first; b <= b_last; b++) {
       const int lc = b - b_first, slot = lc & 1;
       const uint32_t ph = (((uint32_t)lc >> 1) & 1u) ^ 1u;   // first use of each slot passes immediately
-      mbar_wait(smem_u32(&S.cc_free[slot]), ph);
+      mbar_wait(SBARI(cc_free, slot), ph);
       if (lane == 0 && a.in.x_direct == nullptr) pose_inverse(a.in.poses + (size_t)b * 16, S.cc[slot].pinv);
       if (lane < 9) S.cc[slot].T3[lane] = a.T3 ? a.T3[(size_t)b * 9 + lane] : 0.f;
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&S.cc_full[slot]));
+      if (lane == 0) mbar_arrive(SBARI(cc_full, slot));
       if (percand_w1) {
         // per-candidate feature transform as the B operand of L1:  B[j][k] = T64[k][j]   (pointnet2.py:257)
-        mbar_wait(smem_u32(&S.w1_free[slot]), ph);
+        mbar_wait(SBARI(w1_free, slot), ph);
         const float *Tm = a.T64 + (size_t)b * 4096;
         unsigned char *dst = w1 + (size_t)slot * PIECE;
 #pragma unroll 4
@@ -263,7 +268,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         }
         fence_proxy_async();   // generic-proxy writes -> visible to the async proxy (UMMA operand reads)
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&S.w1_full[slot]));
+        if (lane == 0) mbar_arrive(SBARI(w1_full, slot));
       }
     }
   } else if (warp == MMA_WARP || warp == MMAB_WARP) {
@@ -275,34 +280,36 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     // issues the L1 / L2 UMMAs of the next tile at the fixed slots that measured best with one issuer (after chunks 1 and 3;
     // later slots 767 vs 826-850 TFLOP/s, run-time placement by probes 789, a separate issuer for L1 / L2 only 768).
     const bool isB = warp == MMAB_WARP;
-    const uint32_t wb = smem_u32(&S.w_bar);
-    const uint32_t l1b = smem_u32(&S.l1_bar), l2b = smem_u32(&S.l2_bar);
+    const uint32_t wb = SBAR(w_bar);
+    const uint32_t l1b = SBAR(l1_bar), l2b = SBAR(l2_bar);
     uint32_t ph_x1 = 0u, ph_x2 = 0u;
     int b_prev = -1;
     long long t_all = clock64(), t_x3 = 0, t_ring = 0, t_accf = 0, t_x12 = 0, tw;
     // front layers (L1, L2) of local tile `itn` (issuer B only)
+    // issue_l1 is called with consecutive local tiles: (candidate, tile) is a cursor, not a division per call
+    int il_b, il_tile;
+    locate(0, il_b, il_tile);
     auto issue_l1 = [&](int itn) {
-      int b, tile;
-      locate(itn, b, tile);
+      const int b = il_b;
+      const bool last_of_cand = (itn == T - 1) || (il_tile == ntiles - 1);
+      if (++il_tile == ntiles) { il_tile = 0; il_b++; }
       const int lc = b - b_first, slot = percand_w1 ? (lc & 1) : 0;
       const bool new_cand = b != b_prev;
       b_prev = b;
-      int bn, tn;
-      const bool last_of_cand = (itn == T - 1) || (locate(itn + 1, bn, tn), bn != b);
-      if (percand_w1 && new_cand) mbar_wait(smem_u32(&S.w1_full[slot]), ((uint32_t)lc >> 1) & 1u);
-      mbar_wait(smem_u32(&S.x1_bar), ph_x1);
+      if (percand_w1 && new_cand) mbar_wait(SBARI(w1_full, slot), ((uint32_t)lc >> 1) & 1u);
+      mbar_wait(SBAR(x1_bar), ph_x1);
       ph_x1 ^= 1u;
       tc_fence_after();
       if (elect_one()) {
         if (!CG_EXP(a, 8))
           issue_k64(tmem_base + xb_col(itn), xa_s, PIECE, w1_s + (uint32_t)slot * PIECE, 8192u, umma_idesc(128, 64));
         umma_commit(l1b);
-        if (percand_w1 && last_of_cand) umma_commit(smem_u32(&S.w1_free[slot]));
+        if (percand_w1 && last_of_cand) umma_commit(SBARI(w1_free, slot));
       }
       __syncwarp();
     };
     auto issue_l2 = [&](int itn) {
-      mbar_wait(smem_u32(&S.x2_bar), ph_x2);
+      mbar_wait(SBAR(x2_bar), ph_x2);
       ph_x2 ^= 1u;
       tc_fence_after();
       if (elect_one()) {
@@ -314,7 +321,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     // D1 / D2 of tile itn land in the activation block XB(itn) = XB(itn - 2), whose X3 issuer A's chunks of tile itn - 2
     // read: they must have completed (B's own chunks are ordered before by issue order)
     auto guard_xb = [&](int itn) {
-      if (itn >= 2) mbar_wait(smem_u32(&S.a_done[itn & 1]), (((uint32_t)itn >> 1) - 1u) & 1u);
+      if (itn >= 2) mbar_wait(SBARI(a_done, itn & 1), (((uint32_t)itn >> 1) - 1u) & 1u);
     };
     if (isB) {
       if (elect_one()) {
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const int buf = isB ? 1 : 0;
     for (int it = 0; it < T; it++) {
       tw = clock64();
-      mbar_wait(smem_u32(&S.x3_bar), (uint32_t)it & 1u);
+      mbar_wait(SBAR(x3_bar), (uint32_t)it & 1u);
       t_x3 += clock64() - tw;
       const bool tr = (it == T / 2) && lane == 0 && !isB;
       CG_TRACE_AT(tr, 0);
@@ -344,15 +351,15 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         const uint32_t rslot = gidx % NPAIR, rph = (gidx / NPAIR) & 1u;
         if (a.dbg) {   // instrumented run: time the two waits separately
           tw = clock64();
-          if (use >= 1u) mbar_wait(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u);
+          if (use >= 1u) mbar_wait(SBARI(accfree_bar, buf), (use - 1u) & 1u);
           t_accf += clock64() - tw;
           tw = clock64();
-          mbar_wait(smem_u32(&S.full_bar[rslot]), rph);
+          mbar_wait(SBARI(full_bar, rslot), rph);
           t_ring += clock64() - tw;
         } else if (use >= 1u) {
-          mbar_wait2(smem_u32(&S.accfree_bar[buf]), (use - 1u) & 1u, smem_u32(&S.full_bar[rslot]), rph);
+          mbar_wait2(SBARI(accfree_bar, buf), (use - 1u) & 1u, SBARI(full_bar, rslot), rph);
         } else {
-          mbar_wait(smem_u32(&S.full_bar[rslot]), rph);
+          mbar_wait(SBARI(full_bar, rslot), rph);
         }
         tc_fence_after();
         CG_TRACE_AT(tr, 1 + 2 * c);
@@ -368,9 +375,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
                       umma_desc(w_s + (uint32_t)i * PIECE + (uint32_t)ks * 32u), id3, (i | ks) ? 1u : 0u);
             }
           }
-          umma_commit(smem_u32(&S.free_bar[rslot]));
-          umma_commit(smem_u32(&S.acc_bar[buf]));
-          if (!isB && c == NCHUNK - 2) umma_commit(smem_u32(&S.a_done[it & 1]));
+          umma_commit(SBARI(free_bar, rslot));
+          umma_commit(SBARI(acc_bar, buf));
+          if (!isB && c == NCHUNK - 2) umma_commit(SBARI(a_done, it & 1));
         }
         __syncwarp();
         CG_TRACE_AT(tr, 2 + 2 * c);
@@ -405,16 +412,19 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     int b_cur, tile_cur;
     locate(0, b_cur, tile_cur);
     long long m_all = clock64(), m_wait = 0, mw;
+    // Running max of the current candidate: after the lane exchange thread t owns columns 2t, 2t+1 of its warp's 64-column
+    // half of every chunk and keeps them in a PRIVATE shared-memory slot (one LDS.64 / STS.64 per chunk, no atomics, no
+    // key conversion).  Only when the CTA leaves the candidate do the four lane-quarter warps meet: once per candidate
+    // instead of once per tile.
+    bool first = true;   // first tile of the candidate inside this CTA: the slot is overwritten, not merged
     for (int it = 0; it < T; it++) {
-      int b_next = -1, tile_next = 0;
-      if (it + 1 < T) locate(it + 1, b_next, tile_next);
-      uint32_t *gm = S.gmax_s[(b_cur - b_first) & 1];
+      const bool leaving = (it == T - 1) || (tile_cur == ntiles - 1);   // last tile of this candidate inside the CTA's range
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; c++) {
         const int buf = c & 1;
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);
         mw = clock64();
-        mbar_wait(smem_u32(&S.acc_bar[buf]), use & 1u);
+        mbar_wait(SBARI(acc_bar, buf), use & 1u);
         m_wait += clock64() - mw;
         tc_fence_after();
         const bool trm = (it == T / 2) && tid == NFT;
@@ -425,7 +435,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         if (CG_EXP(a, 2)) {   // timing experiment: no TMEM reads, no reduction
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&S.accfree_bar[buf]));
+          if (lane == 0) mbar_arrive(SBARI(accfree_bar, buf));
           continue;
         }
         tmem_ld_16x256b_x8(col0 + lane_lo, ra);
@@ -434,28 +444,45 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         // this warp's part of the accumulator is in registers: hand it back before reducing
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&S.accfree_bar[buf]));
+        if (lane == 0) mbar_arrive(SBARI(accfree_bar, buf));
         CG_TRACE_AT(trm, 25 + 3 * c);
         colmax64_reduce(ra, rb, lane, r0);
-        uint32_t *g = gm + c * 128 + hsel * 64 + 2 * lane;
-        atomicMax(g, cg_f2key(r0[0]));
-        atomicMax(g + 1, cg_f2key(r0[1]));
+        float2 *slot = &S.sacc[c][warp - NFRONT][lane];
+        if (!first) {
+          const float2 old = *slot;
+          r0[0] = fmaxf(r0[0], old.x);
+          r0[1] = fmaxf(r0[1], old.y);
+        }
+        *slot = make_float2(r0[0], r0[1]);
         CG_TRACE_AT(trm, 26 + 3 * c);
       }
-      if (b_next != b_cur) {
-        // last tile of this candidate inside the CTA's range: fold the running max into the global feature
+      first = false;
+      if (leaving) {
+        // fold the candidate's max into the global feature: flush thread (warp w, lane l) takes chunk w, both column
+        // halves, columns 2l, 2l+1 -- four channels, each the max over the four lane-quarter warps
         bar_max();
-        for (int ch = mt; ch < 1024; ch += NMAXW * 32) {
-          float m = cg_key2f(gm[ch]) + __ldg(&a.l3.b[ch]);   // bias is constant over points: add after the max
-          gm[ch] = 0u;
-          if (a.relu3) m = fmaxf(m, 0.f);
-          atomicMax(&a.gmax_keys[(size_t)b_cur * 1024 + ch], cg_f2key(m));
+        const int cw = warp - NFRONT;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float2 m = S.sacc[cw][h * 4][lane];
+#pragma unroll
+          for (int qq = 1; qq < 4; qq++) {
+            const float2 o = S.sacc[cw][h * 4 + qq][lane];
+            m.x = fmaxf(m.x, o.x);
+            m.y = fmaxf(m.y, o.y);
+          }
+          const int ch = cw * 128 + h * 64 + 2 * lane;
+          const float2 bb = __ldg(reinterpret_cast<const float2 *>(&a.l3.b[ch]));   // bias is constant over points: add after the max
+          m.x += bb.x;
+          m.y += bb.y;
+          if (a.relu3) { m.x = fmaxf(m.x, 0.f); m.y = fmaxf(m.y, 0.f); }
+          atomicMax(&a.gmax_keys[(size_t)b_cur * 1024 + ch], cg_f2key(m.x));
+          atomicMax(&a.gmax_keys[(size_t)b_cur * 1024 + ch + 1], cg_f2key(m.y));
         }
-        // no second barrier: the next candidate accumulates into the other buffer, and this buffer's next use lies
-        // behind the next flush barrier
+        bar_max();   // every slot has been read: the next candidate's first tile may overwrite
+        first = true;
       }
-      b_cur = b_next;
-      tile_cur = tile_next;
+      if (++tile_cur == ntiles) { tile_cur = 0; b_cur++; }
     }
     if (a.dbg && tid == NFT) {
       unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       const bool last_of_cand = (it == T - 1) || (l0_tile == ntiles - 1);
       if (++l0_tile == ntiles) { l0_tile = 0; l0_b++; }
       const int lc = b - b_first, slot = lc & 1;
-      if (b != b_l0) mbar_wait(smem_u32(&S.cc_full[slot]), ((uint32_t)lc >> 1) & 1u);
+      if (b != b_l0) mbar_wait(SBARI(cc_full, slot), ((uint32_t)lc >> 1) & 1u);
       b_l0 = b;
       const CandConst &C = S.cc[slot];
       float v[6];
@@ -544,7 +571,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         const int c0 = half * 32 + cc * 8;
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = 0.f;
+        for (int j = 0; j < 8; j++) o[j] = S.bias0[c0 + j];
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           const float4 wa = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0]);
@@ -553,29 +580,29 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           o[4] = fmaf(v[k], wb.x, o[4]); o[5] = fmaf(v[k], wb.y, o[5]); o[6] = fmaf(v[k], wb.z, o[6]); o[7] = fmaf(v[k], wb.w, o[7]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j] + S.bias0[c0 + j], 0.f);
+        for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j], 0.f);
         const uint32_t off = row_chunk_off(p, c0 >> 3);
         store_hilo8(xa + off, xa + PIECE + off, o);
       }
       fence_proxy_async();   // generic-proxy tile writes -> visible to the async proxy (UMMA operand reads)
       bar_front();
       if (tid == 0) {
-        mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
-        if (last_of_cand) mbar_arrive(smem_u32(&S.cc_free[slot]));   // every front thread is past its reads of cc[slot]
+        mbar_arrive((has_l1 ? SBAR(x1_bar) : SBAR(x2_bar)));
+        if (last_of_cand) mbar_arrive(SBARI(cc_free, slot));   // every front thread is past its reads of cc[slot]
       }
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 52);
     };
     // L1 epilogue of local tile `it`: D1 -> (bias, ReLU | nothing) -> XA as the L2 input
     auto l1_epilogue = [&](int it) {
       const long long fw1 = clock64();
-      mbar_wait(smem_u32(&S.l1_bar), (uint32_t)it & 1u);
+      mbar_wait(SBAR(l1_bar), (uint32_t)it & 1u);
       f_l1 += clock64() - fw1;
       tc_fence_after();
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 53);
       if (CG_EXP(a, 4)) {   // timing experiment: front warps skip their math
         tc_fence_before();
         bar_front();
-        if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
+        if (tid == 0) mbar_arrive(SBAR(x2_bar));
         return;
       }
       float v[32];
@@ -602,7 +629,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       tc_fence_before();
       fence_proxy_async();
       bar_front();
-      if (tid == 0) mbar_arrive(smem_u32(&S.x2_bar));
+      if (tid == 0) mbar_arrive(SBAR(x2_bar));
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 54);
     };
 
@@ -617,7 +644,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       const bool has_next = it + 1 < T;
       // A. D2(it) complete; its UMMAs no longer read XA
       fw = clock64();
-      mbar_wait(smem_u32(&S.l2_bar), (uint32_t)it & 1u);
+      mbar_wait(SBAR(l2_bar), (uint32_t)it & 1u);
       f_l2 += clock64() - fw;
       tc_fence_after();
       CG_TRACE_AT(tid == 0 && it == T / 2, 48);
@@ -625,19 +652,19 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       if (CG_EXP(a, 4)) {
         tc_fence_before();
         bar_front();
-        if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
+        if (tid == 0) mbar_arrive(SBAR(x3_bar));
         if (has_next) {
           int b, tile, bn, tn;
           locate(it + 1, b, tile);
           const int lc = b - b_first, slot = lc & 1;
-          if (b != b_l0) mbar_wait(smem_u32(&S.cc_full[slot]), ((uint32_t)lc >> 1) & 1u);
+          if (b != b_l0) mbar_wait(SBARI(cc_full, slot), ((uint32_t)lc >> 1) & 1u);
           b_l0 = b;
           const bool last_of_cand = (it + 1 == T - 1) || (locate(it + 2, bn, tn), bn != b);
           fence_proxy_async();
           bar_front();
           if (tid == 0) {
-            mbar_arrive(smem_u32(has_l1 ? &S.x1_bar : &S.x2_bar));
-            if (last_of_cand) mbar_arrive(smem_u32(&S.cc_free[slot]));
+            mbar_arrive((has_l1 ? SBAR(x1_bar) : SBAR(x2_bar)));
+            if (last_of_cand) mbar_arrive(SBARI(cc_free, slot));
           }
           if (has_l1) l1_epilogue(it + 1);
         }
@@ -667,7 +694,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       tmem_st_wait();
       tc_fence_before();
       bar_front();
-      if (tid == 0) mbar_arrive(smem_u32(&S.x3_bar));
+      if (tid == 0) mbar_arrive(SBAR(x3_bar));
       CG_TRACE_AT(tid == 0 && it == T / 2, 49);
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 56);
       // B. 6 -> 64 of the NEXT tile (inputs were prefetched a tile ago)
