@@ -93,6 +93,15 @@ struct MiscP {
 #define CG_EXP(a, bit) false
 #endif
 
+// per-role cycle counters exist only in developer builds: a release build reads no clocks in the hot loops
+#ifdef CG_EXPERIMENTS
+#define CG_CLK() clock64()
+#define CG_DBG(a) ((a).dbg)
+#else
+#define CG_CLK() 0ll
+#define CG_DBG(a) ((unsigned long long *)nullptr)
+#endif
+
 // developer timeline: clock64 stamps of one steady-state tile of CTA 0 (slot ids are printed by the host side)
 #ifdef CG_EXPERIMENTS
 #define CG_TRACE_AT(cond, slot)                                                     \
@@ -154,7 +163,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
   MiscP &S = *reinterpret_cast<MiscP *>(smem + MISC_OFF);
   // shared-space address of the barrier block, converted once: every barrier operand below is misc_s + a constant
   // (a generic-to-shared conversion per use showed up with 5-7 % of the stall samples)
-  const uint32_t misc_s = smem_u32(smem) + MISC_OFF;
+  uint32_t smem_s = smem_u32(smem);
+  asm volatile("" : "+r"(smem_s));   // opaque: otherwise the compiler re-derives it from SR_CgaCtaId (an S2R) before every use
+  const uint32_t misc_s = smem_s + MISC_OFF;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = a.N;
   // contiguous range of flattened (candidate, tile) work items of this CTA
@@ -206,8 +217,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = S.tmem_base;
-  const uint32_t xa_s = smem_u32(xa), w1_s = smem_u32(w1), w2_s = smem_u32(smem + W2_OFF);
-  const uint32_t ring_s = smem_u32(smem + RING_OFF);
+  const uint32_t xa_s = smem_s + XA_OFF, w1_s = smem_s + W1_OFF, w2_s = smem_s + W2_OFF;
+  const uint32_t ring_s = smem_s + RING_OFF;
 
   // (candidate, tile) of local work item `it`
   auto locate = [&](int it, int &b, int &tile) {
@@ -284,7 +295,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const uint32_t l1b = SBAR(l1_bar), l2b = SBAR(l2_bar);
     uint32_t ph_x1 = 0u, ph_x2 = 0u;
     int b_prev = -1;
-    long long t_all = clock64(), t_x3 = 0, t_ring = 0, t_accf = 0, t_x12 = 0, tw;
+    long long t_all = CG_CLK(), t_x3 = 0, t_ring = 0, t_accf = 0, t_x12 = 0, tw;
     // front layers (L1, L2) of local tile `itn` (issuer B only)
     // issue_l1 is called with consecutive local tiles: (candidate, tile) is a cursor, not a division per call
     int il_b, il_tile;
@@ -338,9 +349,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     constexpr uint32_t id3 = umma_idesc(128, 128, 0u, 0u);   // f16 x f16 -> f32
     const int buf = isB ? 1 : 0;
     for (int it = 0; it < T; it++) {
-      tw = clock64();
+      tw = CG_CLK();
       mbar_wait(SBAR(x3_bar), (uint32_t)it & 1u);
-      t_x3 += clock64() - tw;
+      t_x3 += CG_CLK() - tw;
       const bool tr = (it == T / 2) && lane == 0 && !isB;
       CG_TRACE_AT(tr, 0);
       const bool has_next = it + 1 < T;
@@ -349,13 +360,13 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);   // earlier uses of this accumulator
         const uint32_t gidx = (uint32_t)it * NCHUNK + (uint32_t)c;     // chunk number in the W3 stream
         const uint32_t rslot = gidx % NPAIR, rph = (gidx / NPAIR) & 1u;
-        if (a.dbg) {   // instrumented run: time the two waits separately
-          tw = clock64();
+        if (CG_DBG(a)) {   // instrumented run: time the two waits separately
+          tw = CG_CLK();
           if (use >= 1u) mbar_wait(SBARI(accfree_bar, buf), (use - 1u) & 1u);
-          t_accf += clock64() - tw;
-          tw = clock64();
+          t_accf += CG_CLK() - tw;
+          tw = CG_CLK();
           mbar_wait(SBARI(full_bar, rslot), rph);
-          t_ring += clock64() - tw;
+          t_ring += CG_CLK() - tw;
         } else if (use >= 1u) {
           mbar_wait2(SBARI(accfree_bar, buf), (use - 1u) & 1u, SBARI(full_bar, rslot), rph);
         } else {
@@ -383,22 +394,22 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         CG_TRACE_AT(tr, 2 + 2 * c);
         // front layers of the NEXT tile run in the shadow of this tile's L3 stream (issuer B)
         if (isB && has_next && c == 1 && has_l1) {
-          tw = clock64();
+          tw = CG_CLK();
           guard_xb(it + 1);
           issue_l1(it + 1);
-          t_x12 += clock64() - tw;
+          t_x12 += CG_CLK() - tw;
         }
         if (isB && has_next && c == (has_l1 ? 3 : 1)) {
-          tw = clock64();
+          tw = CG_CLK();
           if (!has_l1) guard_xb(it + 1);
           issue_l2(it + 1);
-          t_x12 += clock64() - tw;
+          t_x12 += CG_CLK() - tw;
         }
       }
     }
-    if (a.dbg && lane == 0) {
+    if (CG_DBG(a) && lane == 0) {
       unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
-      if (!isB) { dd[0] = clock64() - t_all; dd[1] = t_x3; dd[2] = t_ring; dd[3] = t_accf; dd[5] = T; }
+      if (!isB) { dd[0] = CG_CLK() - t_all; dd[1] = t_x3; dd[2] = t_ring; dd[3] = t_accf; dd[5] = T; }
       else dd[4] = t_x12;
     }
   } else if (warp >= NFRONT) {
@@ -411,7 +422,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const int mt = tid - NFT;   // 0..255
     int b_cur, tile_cur;
     locate(0, b_cur, tile_cur);
-    long long m_all = clock64(), m_wait = 0, mw;
+    long long m_all = CG_CLK(), m_wait = 0, mw;
     // Running max of the current candidate: after the lane exchange thread t owns columns 2t, 2t+1 of its warp's 64-column
     // half of every chunk and keeps them in a PRIVATE shared-memory slot (one LDS.64 / STS.64 per chunk, no atomics, no
     // key conversion).  Only when the CTA leaves the candidate do the four lane-quarter warps meet: once per candidate
@@ -423,9 +434,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       for (int c = 0; c < NCHUNK; c++) {
         const int buf = c & 1;
         const uint32_t use = (uint32_t)it * 4u + (uint32_t)(c >> 1);
-        mw = clock64();
+        mw = CG_CLK();
         mbar_wait(SBARI(acc_bar, buf), use & 1u);
-        m_wait += clock64() - mw;
+        m_wait += CG_CLK() - mw;
         tc_fence_after();
         const bool trm = (it == T / 2) && tid == NFT;
         CG_TRACE_AT(trm, 24 + 3 * c);
@@ -484,9 +495,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       }
       if (++tile_cur == ntiles) { tile_cur = 0; b_cur++; }
     }
-    if (a.dbg && tid == NFT) {
+    if (CG_DBG(a) && tid == NFT) {
       unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
-      dd[6] = clock64() - m_all; dd[7] = m_wait;
+      dd[6] = CG_CLK() - m_all; dd[7] = m_wait;
     }
   } else {
     // ======================= front warps: thread = (point, channel half) =======================
@@ -494,7 +505,7 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     const int q = warp & 3;                         // TMEM lane quadrant of this warp
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     float vmax = 0.f;   // largest 128->1024 input seen by this thread (post-ReLU, >= 0): reported if beyond the fp16 range
-    long long f_all = clock64(), f_l2 = 0, f_l1 = 0, fw;
+    long long f_all = CG_CLK(), f_l2 = 0, f_l1 = 0, fw;
     // raw input row of this thread's point for the tile being prepared (prefetched one tile ahead so that the
     // dependent global loads ids -> cloud row are off the critical path between two tiles)
     double rx[6];
@@ -594,9 +605,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     };
     // L1 epilogue of local tile `it`: D1 -> (bias, ReLU | nothing) -> XA as the L2 input
     auto l1_epilogue = [&](int it) {
-      const long long fw1 = clock64();
+      const long long fw1 = CG_CLK();
       mbar_wait(SBAR(l1_bar), (uint32_t)it & 1u);
-      f_l1 += clock64() - fw1;
+      f_l1 += CG_CLK() - fw1;
       tc_fence_after();
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 53);
       if (CG_EXP(a, 4)) {   // timing experiment: front warps skip their math
@@ -643,9 +654,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
     for (int it = 0; it < T; it++) {
       const bool has_next = it + 1 < T;
       // A. D2(it) complete; its UMMAs no longer read XA
-      fw = clock64();
+      fw = CG_CLK();
       mbar_wait(SBAR(l2_bar), (uint32_t)it & 1u);
-      f_l2 += clock64() - fw;
+      f_l2 += CG_CLK() - fw;
       tc_fence_after();
       CG_TRACE_AT(tid == 0 && it == T / 2, 48);
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 55);
@@ -707,9 +718,9 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       if (has_next && has_l1) l1_epilogue(it + 1);
     }
     if (vmax > 65504.f && a.ovf_flag) atomicOr(a.ovf_flag, 1u);
-    if (a.dbg && tid == 0) {
+    if (CG_DBG(a) && tid == 0) {
       unsigned long long *dd = a.dbg + (size_t)blockIdx.x * 16;
-      dd[8] = clock64() - f_all; dd[9] = f_l2; dd[10] = f_l1;
+      dd[8] = CG_CLK() - f_all; dd[9] = f_l2; dd[10] = f_l1;
     }
   }
 
