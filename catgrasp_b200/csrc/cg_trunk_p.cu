@@ -115,7 +115,6 @@ struct MiscP {
 constexpr size_t SMEM_BYTES_P = MISC_OFF + sizeof(MiscP) + 1024;   // + slack for manual 1024-byte alignment
 static_assert(SMEM_BYTES_P <= 232448, "exceeds the 227 KB per-CTA shared memory of sm_100");
 
-__device__ __forceinline__ void bar_front() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void bar_max() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
 // split 8 fp32 values into bf16 hi / lo and store them as the two 16-byte chunks of an operand row
@@ -198,13 +197,13 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       mbar_init(SBARI(acc_bar, i), 1);
       mbar_init(SBARI(accfree_bar, i), NMAXW);
       mbar_init(SBARI(cc_full, i), 1);
-      mbar_init(SBARI(cc_free, i), 1);
+      mbar_init(SBARI(cc_free, i), NFRONT);
       mbar_init(SBARI(w1_full, i), 1);
       mbar_init(SBARI(w1_free, i), 1);
     }
-    mbar_init(SBAR(x1_bar), 1);
-    mbar_init(SBAR(x2_bar), 1);
-    mbar_init(SBAR(x3_bar), 1);
+    mbar_init(SBAR(x1_bar), NFRONT);   // front -> issuer hand-overs: one arrival per front warp (no block barrier first)
+    mbar_init(SBAR(x2_bar), NFRONT);
+    mbar_init(SBAR(x3_bar), NFRONT);
     mbar_init(SBAR(l1_bar), 1);
     mbar_init(SBAR(l2_bar), 1);
     mbar_init(SBAR(w_bar), 1);
@@ -381,8 +380,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           for (int i = 0; i < (CG_EXP(a, 16) ? 0 : 2); i++) {
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
-              // D3[pt][ch] += X3[pt][k] (TMEM, 8 packed columns per K-step) . W3[ch][k] (smem)
-              umma_ts(d, x3c + (uint32_t)i * 32u + (uint32_t)ks * 8u,
+              // D3[pt][ch] += X3[pt][k] (TMEM, 8 packed columns per K-step, K-block i at column i*64) . W3[ch][k] (smem)
+              umma_ts(d, x3c + (uint32_t)i * 64u + (uint32_t)ks * 8u,
                       umma_desc(w_s + (uint32_t)i * PIECE + (uint32_t)ks * 32u), id3, (i | ks) ? 1u : 0u);
             }
           }
@@ -596,10 +595,10 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         store_hilo8(xa + off, xa + PIECE + off, o);
       }
       fence_proxy_async();   // generic-proxy tile writes -> visible to the async proxy (UMMA operand reads)
-      bar_front();
-      if (tid == 0) {
+      __syncwarp();
+      if (lane == 0) {
         mbar_arrive((has_l1 ? SBAR(x1_bar) : SBAR(x2_bar)));
-        if (last_of_cand) mbar_arrive(SBARI(cc_free, slot));   // every front thread is past its reads of cc[slot]
+        if (last_of_cand) mbar_arrive(SBARI(cc_free, slot));   // this warp is past its reads of cc[slot]
       }
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 52);
     };
@@ -612,8 +611,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 53);
       if (CG_EXP(a, 4)) {   // timing experiment: front warps skip their math
         tc_fence_before();
-        bar_front();
-        if (tid == 0) mbar_arrive(SBAR(x2_bar));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(SBAR(x2_bar));
         return;
       }
       float v[32];
@@ -639,8 +638,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       }
       tc_fence_before();
       fence_proxy_async();
-      bar_front();
-      if (tid == 0) mbar_arrive(SBAR(x2_bar));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(SBAR(x2_bar));
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 54);
     };
 
@@ -662,8 +661,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 55);
       if (CG_EXP(a, 4)) {
         tc_fence_before();
-        bar_front();
-        if (tid == 0) mbar_arrive(SBAR(x3_bar));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(SBAR(x3_bar));
         if (has_next) {
           int b, tile, bn, tn;
           locate(it + 1, b, tile);
@@ -672,8 +671,8 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           b_l0 = b;
           const bool last_of_cand = (it + 1 == T - 1) || (locate(it + 2, bn, tn), bn != b);
           fence_proxy_async();
-          bar_front();
-          if (tid == 0) {
+          __syncwarp();
+          if (lane == 0) {
             mbar_arrive((has_l1 ? SBAR(x1_bar) : SBAR(x2_bar)));
             if (last_of_cand) mbar_arrive(SBARI(cc_free, slot));
           }
@@ -696,16 +695,14 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
           asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ph[j32 * 16 + j]) : "f"(a1), "f"(a0));
         }
       }
-      // word j of this thread = channels (half*64 + 2j, +1) of its point = packed K column half*32 + j;
-      // every front thread must have pulled its fp32 half-row out of D2 before the block is overwritten
-      tc_fence_before();
-      bar_front();
-      tc_fence_after();
-      tmem_st32(tmem_base + lane_sel + xb_col(it) + (uint32_t)half * 32u, ph);
+      // word j of this thread = channels (half*64 + 2j, +1) of its point.  The packed row goes back into the first 32 of
+      // the 64 columns this thread has just read (K-block `half` of X3 lives at column half*64): no other thread reads
+      // or writes them, so no block barrier separates the D2 reads from the X3 writes
+      tmem_st32(tmem_base + lane_sel + xb_col(it) + (uint32_t)half * 64u, ph);
       tmem_st_wait();
       tc_fence_before();
-      bar_front();
-      if (tid == 0) mbar_arrive(SBAR(x3_bar));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(SBAR(x3_bar));
       CG_TRACE_AT(tid == 0 && it == T / 2, 49);
       CG_TRACE_AT(tid == 0 && it == T / 2 + 1, 56);
       // B. 6 -> 64 of the NEXT tile (inputs were prefetched a tile ago)
