@@ -124,8 +124,8 @@ __device__ __forceinline__ void store_hilo8(unsigned char *hi_dst, unsigned char
   for (int j = 0; j < 4; j++) {
     const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
     const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hh);
-    const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
-    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - h0, v[2 * j + 1] - h1);
+    const float2 lo = fsub2(make_float2(v[2 * j], v[2 * j + 1]), make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u)));
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(lo.x, lo.y);
     h[j] = hb;
     l[j] = *reinterpret_cast<const uint32_t *>(&ll);
   }
@@ -580,17 +580,24 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       for (int cc = 0; cc < 4; cc++) {
         const int c0 = half * 32 + cc * 8;
         float o[8];
+        float2 o2[4];   // channel pairs: FFMA2 does two of the 6 -> 64 multiply-adds per issue slot
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = S.bias0[c0 + j];
+        for (int j = 0; j < 4; j++) o2[j] = *reinterpret_cast<const float2 *>(&S.bias0[c0 + 2 * j]);
 #pragma unroll
         for (int k = 0; k < 6; k++) {
           const float4 wa = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0]);
           const float4 wb = *reinterpret_cast<const float4 *>(&S.w0[k * 64 + c0 + 4]);
-          o[0] = fmaf(v[k], wa.x, o[0]); o[1] = fmaf(v[k], wa.y, o[1]); o[2] = fmaf(v[k], wa.z, o[2]); o[3] = fmaf(v[k], wa.w, o[3]);
-          o[4] = fmaf(v[k], wb.x, o[4]); o[5] = fmaf(v[k], wb.y, o[5]); o[6] = fmaf(v[k], wb.z, o[6]); o[7] = fmaf(v[k], wb.w, o[7]);
+          const float2 vv = make_float2(v[k], v[k]);
+          o2[0] = ffma2(vv, make_float2(wa.x, wa.y), o2[0]);
+          o2[1] = ffma2(vv, make_float2(wa.z, wa.w), o2[1]);
+          o2[2] = ffma2(vv, make_float2(wb.x, wb.y), o2[2]);
+          o2[3] = ffma2(vv, make_float2(wb.z, wb.w), o2[3]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) o[j] = fmaxf(o[j], 0.f);
+        for (int j = 0; j < 4; j++) {
+          o[2 * j] = fmaxf(o2[j].x, 0.f);
+          o[2 * j + 1] = fmaxf(o2[j].y, 0.f);
+        }
         const uint32_t off = row_chunk_off(p, c0 >> 3);
         store_hilo8(xa + off, xa + PIECE + off, o);
       }
@@ -619,7 +626,11 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
       tmem_ld32(tmem_base + lane_sel + xb_col(it) + (uint32_t)half * 32u, v);
       if (a.stage1_mode == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j] + S.bias1[half * 32 + j], 0.f);
+        for (int j = 0; j < 16; j++) {
+          const float2 t = fadd2(make_float2(v[2 * j], v[2 * j + 1]), *reinterpret_cast<const float2 *>(&S.bias1[half * 32 + 2 * j]));
+          v[2 * j] = fmaxf(t.x, 0.f);
+          v[2 * j + 1] = fmaxf(t.y, 0.f);
+        }
       }
       if (a.pf_out) {   // PointNetSeg point feature (pointnet2.py:261)
         int b, tile;
@@ -688,11 +699,12 @@ __global__ void __launch_bounds__(NTP, 1) trunk_p_kernel(const cg_trunk_args a, 
         tmem_ld32(tmem_base + lane_sel + xb_col(it) + (uint32_t)half * 64u + (uint32_t)j32 * 32u, v);
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-          const float a0 = fmaxf(v[2 * j] + S.bias2[half * 64 + j32 * 32 + 2 * j], 0.f);
-          const float a1 = fmaxf(v[2 * j + 1] + S.bias2[half * 64 + j32 * 32 + 2 * j + 1], 0.f);
-          vmax = fmax3(vmax, a0, a1);
-          // F2FP.SATFINITE: values beyond the fp16 range saturate to 65504 instead of becoming inf (a0 -> low half)
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ph[j32 * 16 + j]) : "f"(a1), "f"(a0));
+          const float2 t = fadd2(make_float2(v[2 * j], v[2 * j + 1]),
+                                 *reinterpret_cast<const float2 *>(&S.bias2[half * 64 + j32 * 32 + 2 * j]));
+          vmax = fmax3(vmax, t.x, t.y);   // vmax >= 0: negative sums (ReLU'd to 0 below) cannot raise it
+          // F2FP.RELU.SATFINITE: ReLU inside the conversion; values beyond the fp16 range saturate to 65504 instead of
+          // becoming inf (t.x -> low half)
+          asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(ph[j32 * 16 + j]) : "f"(t.y), "f"(t.x));
         }
       }
       // word j of this thread = channels (half*64 + 2j, +1) of its point.  The packed row goes back into the first 32 of
