@@ -177,8 +177,9 @@ struct HitQueue {
   int count[2];
 };
 
+// Scans points pts[0], pts[stride], ..., pts[(P-1)*stride] (rows of 3 floats).
 __device__ bool any_point_hits(const SdfView &s, const float *G, int mode, float margin, const float *__restrict__ pts, int P,
-                               volatile int *flag, HitQueue &Q) {
+                               int stride, volatile int *flag, HitQueue &Q) {
   // four independent points per thread and iteration (12 loads in flight) -- the loop is latency-bound otherwise;
   // within one j the 256 threads read consecutive points (coalesced 12-byte rows)
   if (!(mode == CG_SDF_TRILINEAR && s.border_nonneg)) {
@@ -190,7 +191,7 @@ __device__ bool any_point_hits(const SdfView &s, const float *G, int mode, float
       for (int j = 0; j < 4; j++) {
         const int p = base + j * FT + threadIdx.x;
         ok[j] = p < P;
-        const size_t o = 3 * (size_t)(ok[j] ? p : 0);
+        const size_t o = 3 * (size_t)(ok[j] ? p : 0) * (size_t)stride;
         x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
       }
 #pragma unroll
@@ -217,7 +218,7 @@ __device__ bool any_point_hits(const SdfView &s, const float *G, int mode, float
     for (int j = 0; j < 4; j++) {
       const int p = base + j * FT + threadIdx.x;
       ok[j] = p < P;
-      const size_t o = 3 * (size_t)(ok[j] ? p : 0);
+      const size_t o = 3 * (size_t)(ok[j] ? p : 0) * (size_t)stride;
       x[j] = __ldg(pts + o); y[j] = __ldg(pts + o + 1); z[j] = __ldg(pts + o + 2);
     }
 #pragma unroll
@@ -309,15 +310,16 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
     __syncthreads();
     // The verdict is (open gripper hits the object's points) OR (swept gripper hits the background points), so the
     // order of the scans is free (the reference does open first, common.cpp:268-278).  In clutter nearly every rejection
-    // comes from the background and shows up within the first points scanned, whereas the object's own points all lie
-    // inside the gripper's grid box (every one needs the eight-corner lookup) and never end the scan early.  So: the
-    // head of the background set, then the object set, then the rest of the background.  (`flag` is only ever set by a
-    // hit, so it is still clear whenever a later scan starts.)
+    // comes from the background and shows up within a few hundred well-spread background points, whereas the object's own
+    // points all lie inside the gripper's grid box (every one needs the eight-corner lookup) and never end the scan
+    // early.  So: a strided sample of the background (every (P2/1024)-th point: spatially uniform whatever order the
+    // caller's points come in -- raster order of an occupancy image, sorted, shuffled), then the object set, then the
+    // whole background.  (`flag` is only ever set by a hit, so it is still clear whenever a later scan starts.)
     const int head = min(P2, 4 * FT);
-    bool coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, head, &flag, hq);
-    if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, prm.sdf_margin, open_pts, P1, &flag, hq);
-    if (!coll && P2 > head)
-      coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts + 3 * (size_t)head, P2 - head, &flag, hq);
+    const int hstride = head > 0 ? P2 / head : 1;
+    bool coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, head, hstride, &flag, hq);
+    if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, prm.sdf_margin, open_pts, P1, 1, &flag, hq);
+    if (!coll && P2 > head) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, P2, 1, &flag, hq);
     if (!coll) { winner = k; break; }
     __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
   }

@@ -6,9 +6,10 @@ import bench
 from catgrasp_b200 import my_cpp
 from catgrasp_b200.sdf import Sdf3D
 
-args = types.SimpleNamespace(candidates=4096, n_pts=1024, scene_pts=20000, nunocs_pts=8192, gpus=1)
-wl = bench.make_workload(args, 0)
-g = wl["gripper"]
+from catgrasp_b200.synthetic import make_gripper_proxy
+args = types.SimpleNamespace(n_pts=1024, nunocs_pts=8192, gpus=1)
+wl = bench.make_scene_job("K2", 0, 0, 4096, 4096, args, 0)
+g = make_gripper_proxy()
 so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
 se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
 dev = torch.device("cuda", 0)
@@ -44,4 +45,7 @@ for name, pts in (("bg", d_bg),):
     timed(pts[torch.argsort(d2)].contiguous(), d_open, "bg sorted by distance to the object centroid")
     timed(pts[torch.argsort(d2, descending=True)].contiguous(), d_open, "bg sorted far-first (worst case)")
     timed(pts[torch.randperm(pts.shape[0], device=dev)].contiguous(), d_open, "bg shuffled")
+    # raster order of an occupancy image: rows of constant y (1 mm bins), x ascending inside a row
+    key = torch.floor(pts[:, 1].double() * 1000.0) * 1e6 + pts[:, 0].double()
+    timed(pts[torch.argsort(key)].contiguous(), d_open, "bg in raster order (y rows, x ascending)")
 print(f"filter: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per call; accepted {(st == 0).sum().item()}, offsets {np.bincount(off.cpu().numpy().astype(np.int64) + 1).tolist()}, checksum {int(st.sum().item())}")
