@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcatgrasp_b200.so")
 CG_OK, CG_EINVAL, CG_ECUDA, CG_ENOMEM, CG_EUNSUPPORTED = 0, -1, -2, -3, -4
 CG_NET_CLS, CG_NET_SEG = 0, 1
 CG_SDF_TRILINEAR, CG_SDF_NEAREST = 0, 1
-CG_ST_ACCEPT, CG_ST_REJ_DIR, CG_ST_REJ_IK, CG_ST_REJ_COLL = 0, 1, 2, 3
+CG_ST_ACCEPT, CG_ST_REJ_DIR, CG_ST_REJ_IK, CG_ST_REJ_COLL, CG_ST_REJ_COLL_ENCL = 0, 1, 2, 3, 4
 
 
 class CgError(RuntimeError):
@@ -29,6 +29,7 @@ class FilterParams(C.Structure):
         ("adjust_collision_pose", C.c_int),
         ("sdf_mode", C.c_int),
         ("sdf_margin", C.c_float),
+        ("split_coll_status", C.c_int),
     ]
 
 

@@ -291,6 +291,8 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
   const float step1 = 0.001f;
   const float step2 = __fadd_rn(step1, 0.001f);
   const int n_off = prm.adjust_collision_pose ? 5 : 1;
+  const bool split = prm.split_coll_status && !prm.adjust_collision_pose;
+  bool open_hit = false;
   int winner = -1;
   for (int k = 0; k < n_off; k++) {
     if (threadIdx.x == 0) {
@@ -317,14 +319,22 @@ __global__ void __launch_bounds__(FT) filter_kernel(const cg_filter_params prm, 
     // whole background.  (`flag` is only ever set by a hit, so it is still clear whenever a later scan starts.)
     const int head = min(P2, 4 * FT);
     const int hstride = head > 0 ? P2 / head : 1;
-    bool coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, head, hstride, &flag, hq);
-    if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, prm.sdf_margin, open_pts, P1, 1, &flag, hq);
+    bool coll;
+    if (split) {
+      // the caller wants to know WHICH test rejected (verbose counters): the reference's order, open gripper first
+      coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, prm.sdf_margin, open_pts, P1, 1, &flag, hq);
+      open_hit = coll;
+      if (!coll && head > 0) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, head, hstride, &flag, hq);
+    } else {
+      coll = (head > 0) && any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, head, hstride, &flag, hq);
+      if (!coll) coll = any_point_hits(sdf_open, go_s, prm.sdf_mode, prm.sdf_margin, open_pts, P1, 1, &flag, hq);
+    }
     if (!coll && P2 > head) coll = any_point_hits(sdf_encl, ge_s, prm.sdf_mode, prm.sdf_margin, encl_pts, P2, 1, &flag, hq);
     if (!coll) { winner = k; break; }
     __syncthreads();  // everyone is done reading inv_s / flag before thread 0 rewrites them
   }
   if (threadIdx.x == 0) {
-    out_status[q] = (winner >= 0) ? CG_ST_ACCEPT : CG_ST_REJ_COLL;
+    out_status[q] = (winner >= 0) ? CG_ST_ACCEPT : ((split && !open_hit) ? CG_ST_REJ_COLL_ENCL : CG_ST_REJ_COLL);
     out_offset[q] = (int8_t)winner;
   }
   if (threadIdx.x < 16) out_poses[q * 16 + threadIdx.x] = (winner >= 0) ? cur_s[threadIdx.x] : 0.f;

@@ -71,8 +71,10 @@ def _m16(m):
 
 def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_in_grasp,
                           filter_approach_dir_face_camera, adjust_collision_pose, sdf_open, open_pts,
-                          sdf_enclosed, enclosed_pts, sdf_mode=None, device_out=False, sdf_margin=0.0):
-    """Array-level entry: returns (status (Q,) u8, offset (Q,) i8, poses (Q,4,4) f32) with Q = G*S."""
+                          sdf_enclosed, enclosed_pts, sdf_mode=None, device_out=False, sdf_margin=0.0, split_status=False):
+    """Array-level entry: returns (status (Q,) u8, offset (Q,) i8, poses (Q,4,4) f32) with Q = G*S.
+    ``split_status`` (only meaningful without pose adjustment): CG_ST_REJ_COLL = open gripper vs object points,
+    CG_ST_REJ_COLL_ENCL = enclosed gripper vs background (the reference's two verbose counters)."""
     ctx = sdf_open.ctx
     prm = _lib.FilterParams()
     prm.nocs_pose = _m16(nocs_pose)
@@ -82,6 +84,7 @@ def filter_grasp_pose_raw(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_noc
     prm.adjust_collision_pose = int(bool(adjust_collision_pose))
     prm.sdf_mode = DEFAULT_SDF_MODE if sdf_mode is None else int(sdf_mode)
     prm.sdf_margin = float(sdf_margin)
+    prm.split_coll_status = int(bool(split_status))
     if isinstance(grasp_poses, torch.Tensor) and grasp_poses.is_cuda:
         dev = grasp_poses.device
         gp = grasp_poses.to(torch.float32).contiguous().reshape(-1, 16)
@@ -165,23 +168,29 @@ def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_tran
         filter_approach_dir_face_camera, adjust_collision_pose, sdf_open,
         np.asarray(gripper_collision_pts).reshape(-1, 3), sdf_encl,
         np.asarray(gripper_enclosed_collision_pts).reshape(-1, 3),
-        sdf_margin=voxel_margin(octo_resolution) if COLLISION_PREDICATE == "voxel" else 0.0)
+        sdf_margin=voxel_margin(octo_resolution) if COLLISION_PREDICATE == "voxel" else 0.0, split_status=bool(verbose))
     keep = status == _lib.CG_ST_ACCEPT
-    n_ik = 0
+    ik_fail = np.zeros(status.shape[0], bool)
     if filter_ik:
-        # common.cpp:214-226: IK is evaluated on the UN-shifted grasp_in_cam; the approach / IK / collision
-        # tests are independent rejections, so running IK on the collision survivors keeps the same set.
+        # common.cpp:214-226: IK is evaluated on the UN-shifted grasp_in_cam, after the approach test and before the
+        # collision tests.  The rejections are independent, so running IK on the collision survivors only keeps the
+        # same set; verbose mode evaluates it wherever the reference does, so that its counters come out the same.
         cam = np.asarray(cam_in_world, np.float64).astype(np.float32)
         eeg = np.asarray(ee_in_grasp, np.float64).astype(np.float32)
         unshifted = grasp_in_cam_unshifted(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs_transform)
-        for q in np.nonzero(keep)[0]:
+        todo = np.nonzero(status != _lib.CG_ST_REJ_DIR)[0] if verbose else np.nonzero(keep)[0]
+        for q in todo:
             ee_in_base = _mm4_f32(_mm4_f32(cam, unshifted[q]), eeg)      # common.cpp:216, left to right
             if not _IK_SOLVER(ee_in_base, upper, lower):
-                keep[q] = False
-                n_ik += 1
+                ik_fail[q] = True
+        keep &= ~ik_fail
     if verbose:
+        # common.cpp:199-294: a pose is counted by the FIRST test that rejects it (approach, IK, open gripper, enclosed
+        # gripper); with pose adjustment every collision rejection is counted as "open" (:290-294)
+        coll_open = (status == _lib.CG_ST_REJ_COLL) & ~ik_fail
+        coll_encl = (status == _lib.CG_ST_REJ_COLL_ENCL) & ~ik_fail
         print("n_approach_dir_rej={}, n_ik_rej={}, n_open_gripper_rej={}, n_close_gripper_rej={}".format(
-            int((status == _lib.CG_ST_REJ_DIR).sum()), n_ik, int((status == _lib.CG_ST_REJ_COLL).sum()), 0))
+            int((status == _lib.CG_ST_REJ_DIR).sum()), int(ik_fail.sum()), int(coll_open.sum()), int(coll_encl.sum())))
     return [poses[q].copy() for q in np.nonzero(keep)[0]]
 
 

@@ -200,7 +200,8 @@ int cg_sdf_lookup_dev(cg_sdf *sdf, const float *grid_coords, int P, int mode,
 #define CG_ST_ACCEPT    0
 #define CG_ST_REJ_DIR   1
 #define CG_ST_REJ_IK    2
-#define CG_ST_REJ_COLL  3
+#define CG_ST_REJ_COLL  3   /* collision (with split_coll_status and no pose adjustment: the OPEN gripper hits the object) */
+#define CG_ST_REJ_COLL_ENCL 4   /* split_coll_status only: the open gripper is free, the ENCLOSED gripper hits the background */
 typedef struct cg_filter_params {
   float nocs_pose[16];
   float canonical_to_nocs[16];
@@ -214,6 +215,12 @@ typedef struct cg_filter_params {
                               (my_cpp/collision_manager.cpp:93-111): every occupied voxel cube of side
                               octo_resolution that can touch the gripper surface has its generating point within
                               that distance of the surface.                                                        */
+  int   split_coll_status; /* != 0 and adjust_collision_pose == 0: report which of the reference's two tests rejected a
+                              pose (CG_ST_REJ_COLL = open gripper vs object points, common.cpp:231-238;
+                              CG_ST_REJ_COLL_ENCL = enclosed gripper vs background, :241-248) -- the verbose counters
+                              n_open_gripper_rej / n_close_gripper_rej.  Costs the reference's scan order (open first)
+                              instead of the faster background-sample-first order.  With pose adjustment the reference
+                              itself counts every collision rejection as "open" (:290-294): always CG_ST_REJ_COLL.     */
 } cg_filter_params;
 
 int cg_filter_grasp_pose_host(cg_ctx *ctx, const cg_filter_params *prm,

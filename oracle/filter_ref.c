@@ -156,9 +156,12 @@ int gripper_hits_ref(const float *gripper_in_cam, const float *grid, const int *
   return any_hits(&s, g, mode, 0.f, pts, P);
 }
 
-/* status: 0 accept, 1 approach-direction reject, 3 collision reject; offset: 0..4 or -1 */
-void filter_ref_m(const float *nocs_pose, const float *canonical_to_nocs, const float *gripper_in_grasp,
-                int filter_dir, int adjust, int sdf_mode, float sdf_margin, const float *grasp_poses, int G, const float *sym, int S,
+/* status: 0 accept, 1 approach-direction reject, 3 collision reject; offset: 0..4 or -1.
+ * split != 0 and adjust == 0: 3 = the open gripper hits the object's points (common.cpp:231-238, n_open_gripper_rej),
+ * 4 = only the enclosed gripper hits the background (:241-248, n_close_gripper_rej).  With adjust != 0 the reference
+ * counts every collision rejection as n_open_gripper_rej (:290-294): always 3. */
+void filter_ref_ms(const float *nocs_pose, const float *canonical_to_nocs, const float *gripper_in_grasp,
+                int filter_dir, int adjust, int sdf_mode, float sdf_margin, int split, const float *grasp_poses, int G, const float *sym, int S,
                 const float *grid_open, const int *dims_open, const float *origin_open, float res_open,
                 const float *open_pts, int P1, const float *grid_encl, const int *dims_encl,
                 const float *origin_encl, float res_encl, const float *encl_pts, int P2, int nthreads,
@@ -199,7 +202,7 @@ void filter_ref_m(const float *nocs_pose, const float *canonical_to_nocs, const 
       }
     }
     const int n_off = adjust ? 5 : 1;
-    int winner = -1;
+    int winner = -1, open_hit = 0;
     float cur[16];
     for (int k = 0; k < n_off; k++) { /* :253-287 */
       const float step = (k == 0) ? 0.f : ((k <= 2) ? step1 : step2);
@@ -212,13 +215,25 @@ void filter_ref_m(const float *nocs_pose, const float *canonical_to_nocs, const 
       fold_grid(inv, &so, go);
       fold_grid(inv, &se, ge);
       int coll = any_hits(&so, go, sdf_mode, sdf_margin, open_pts, P1);
+      open_hit = coll;
       if (!coll && P2 > 0) coll = any_hits(&se, ge, sdf_mode, sdf_margin, encl_pts, P2);
       if (!coll) { winner = k; break; }
     }
-    out_status[q] = (winner >= 0) ? 0 : 3;
+    out_status[q] = (winner >= 0) ? 0 : ((split && !adjust && !open_hit) ? 4 : 3);
     out_offset[q] = (int8_t)winner;
     if (winner >= 0) memcpy(op, cur, 64); else memset(op, 0, 64); /* :289-293 */
   }
+}
+
+void filter_ref_m(const float *nocs_pose, const float *canonical_to_nocs, const float *gripper_in_grasp,
+                int filter_dir, int adjust, int sdf_mode, float sdf_margin, const float *grasp_poses, int G, const float *sym, int S,
+                const float *grid_open, const int *dims_open, const float *origin_open, float res_open,
+                const float *open_pts, int P1, const float *grid_encl, const int *dims_encl,
+                const float *origin_encl, float res_encl, const float *encl_pts, int P2, int nthreads,
+                uint8_t *out_status, int8_t *out_offset, float *out_poses) {
+  filter_ref_ms(nocs_pose, canonical_to_nocs, gripper_in_grasp, filter_dir, adjust, sdf_mode, sdf_margin, 0, grasp_poses, G, sym, S,
+                grid_open, dims_open, origin_open, res_open, open_pts, P1, grid_encl, dims_encl, origin_encl, res_encl,
+                encl_pts, P2, nthreads, out_status, out_offset, out_poses);
 }
 
 /* point-wise lookups for the SDF parity tests: mode 0 trilinear, 1 nearest (clamped) */

@@ -27,7 +27,7 @@ def _f32(a, shape=None):
 
 
 def filter_ref(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_in_grasp, filter_dir, adjust,
-               sdf_mode, sdf_open, open_pts, sdf_encl, encl_pts, nthreads=0, margin=0.0):
+               sdf_mode, sdf_open, open_pts, sdf_encl, encl_pts, nthreads=0, margin=0.0, split=False):
     """sdf_* = dict(sdf=(nx,ny,nz) f32, origin=(3,), res=float).  Returns (status u8, offset i8, poses f32 (Q,4,4))."""
     lib = _load()
     gp = _f32(grasp_poses, (-1, 16)); st = _f32(symmetry_tfs, (-1, 16))
@@ -42,9 +42,9 @@ def filter_ref(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_
         de = np.array(ge.shape, dtype=np.int32); oe = _f32(sdf_encl["origin"]); re = float(np.float32(sdf_encl["res"]))
     else:
         ge = de = oe = None; re = 1.0
-    lib.filter_ref_m(_p(_f32(nocs_pose, 16)), _p(_f32(canonical_to_nocs, 16)), _p(_f32(gripper_in_grasp, 16)),
+    lib.filter_ref_ms(_p(_f32(nocs_pose, 16)), _p(_f32(canonical_to_nocs, 16)), _p(_f32(gripper_in_grasp, 16)),
                    C.c_int(int(filter_dir)), C.c_int(int(adjust)), C.c_int(int(sdf_mode)), C.c_float(float(np.float32(margin))),
-                   _p(gp), C.c_int(G), _p(st),
+                   C.c_int(int(bool(split))), _p(gp), C.c_int(G), _p(st),
                    C.c_int(S), _p(go), _p(do), _p(oo), C.c_float(float(np.float32(sdf_open["res"]))), _p(p1),
                    C.c_int(p1.shape[0]), _p(ge), _p(de), _p(oe), C.c_float(re), _p(p2), C.c_int(p2.shape[0]),
                    C.c_int(int(nthreads)), _p(status), _p(offset), _p(poses))

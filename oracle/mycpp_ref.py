@@ -38,10 +38,32 @@ def _f32(a, shape=None):
 
 def filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_in_grasp, filter_dir, adjust,
                     sdf_mode, sdf_open, open_pts, sdf_encl, encl_pts, cam_in_world=None, ee_in_grasp=None,
-                    filter_ik=False, upper=None, lower=None, octo_resolution=0.0005):
+                    filter_ik=False, upper=None, lower=None, octo_resolution=0.0005, counters=False):
     """The reference's filterGraspPose (common.cpp:156-321): returns the survivors (K,4,4) float32 in the (thread-order
-    dependent) order the reference produced them."""
+    dependent) order the reference produced them.  ``counters=True`` runs it verbose and also returns the four rejection
+    counters it prints (common.cpp:316-319) as a dict."""
     lib = _load()
+    if counters:
+        import os
+        import re
+        import tempfile
+        lib.ref_set_verbose(C.c_int(1))
+        with tempfile.TemporaryFile(mode="w+b") as tf:
+            saved = os.dup(1)
+            try:
+                os.dup2(tf.fileno(), 1)
+                out = filterGraspPose(grasp_poses, symmetry_tfs, nocs_pose, canonical_to_nocs, gripper_in_grasp, filter_dir,
+                                      adjust, sdf_mode, sdf_open, open_pts, sdf_encl, encl_pts, cam_in_world, ee_in_grasp,
+                                      filter_ik, upper, lower, octo_resolution)
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
+                lib.ref_set_verbose(C.c_int(0))
+            tf.seek(0)
+            txt = tf.read().decode()
+        m = re.search(r"n_approach_dir_rej=(\d+), n_ik_rej=(\d+), n_open_gripper_rej=(\d+), n_close_gripper_rej=(\d+)", txt)
+        assert m, f"the reference printed no counters: {txt!r}"
+        return out, dict(zip(("approach", "ik", "open", "close"), map(int, m.groups())))
     gp = _f32(grasp_poses, (-1, 16)); st = _f32(symmetry_tfs, (-1, 16))
     p1 = _f32(open_pts, (-1, 3)); p2 = _f32(encl_pts, (-1, 3))
     keep = []

@@ -1,5 +1,6 @@
 // extern "C" entry points into the oracle/_ref build of the reference's my_cpp/common.cpp (plain pointers, row-major
 // float32 matrices), for oracle/mycpp_ref.py.  ORACLE / test infrastructure only.
+#include <cstdio>
 #include "common.h"
 #include "collision_manager.h"
 
@@ -24,6 +25,11 @@ void put4(const Eigen::Matrix4f &m, float *p) {
 }
 }  // namespace
 
+// verbose switch of the next ref_filterGraspPose calls: the reference then prints its four rejection counters
+// (common.cpp:316-319) to stdout, which oracle/mycpp_ref.py captures
+static int g_verbose = 0;
+extern "C" void ref_set_verbose(int v) { g_verbose = v; }
+
 // common.h:60.  Meshes are passed as vertex counts only (the shim keys the SDF on them).  Returns the survivor count;
 // at most `cap` poses are written.
 extern "C" int ref_filterGraspPose(const float *grasp_poses, int G, const float *symmetry_tfs, int S, const float *nocs_pose,
@@ -40,7 +46,8 @@ extern "C" int ref_filterGraspPose(const float *grasp_poses, int G, const float 
   Eigen::MatrixXi F = Eigen::MatrixXi::Zero(1, 3);
   vectorMatrix4f out = filterGraspPose(gp, st, m4(nocs_pose), m4(canonical_to_nocs), m4(cam_in_world), m4(ee_in_grasp),
                                        m4(gripper_in_grasp), filter_dir != 0, filter_ik != 0, adjust != 0, up, lo, oV, F, eV, F,
-                                       mx(open_pts, P1, 3), mx(encl_pts, P2, 3), octo_resolution, false);
+                                       mx(open_pts, P1, 3), mx(encl_pts, P2, 3), octo_resolution, g_verbose != 0);
+  if (g_verbose) fflush(stdout);
   for (size_t i = 0; i < out.size() && (int)i < cap; i++) put4(out[i], out_poses + i * 16);
   return (int)out.size();
 }

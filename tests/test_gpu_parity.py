@@ -276,6 +276,47 @@ def test_filter_bit_exact_vs_oracle(cuda, mode, adjust, fdir, S, scale):
 
 
 @pytest.mark.parametrize("mode", [0, 1])
+def test_filter_split_collision_status_vs_oracle(cuda, mode, capsys):
+    """split_coll_status without pose adjustment: which of the reference's two tests rejected a pose (open gripper vs
+    object points -> 3, enclosed gripper vs background -> 4; common.cpp:228-249), bit-exact vs the oracle (whose counters
+    equal the reference build's own, tests/test_mycpp_golden.py); the accept set does not depend on the switch, and
+    filterGraspPose(verbose=True) prints the reference's counter line."""
+    from catgrasp_b200 import my_cpp
+    from catgrasp_b200.sdf import Sdf3D
+    from oracle import filter_ref
+    p1, p2, poses, sym, nocs_pose, c2n, g = _filter_case(43, 256, 2)
+    poses = poses.copy()
+    poses[::3, :3, 3] += poses[::3, :3, 0] * 0.02      # every third candidate 2 cm sideways: a finger lands in the object
+    so = Sdf3D(g["open"]["sdf"], g["open"]["origin"], g["open"]["res"])
+    se = Sdf3D(g["enclosed"]["sdf"], g["enclosed"]["origin"], g["enclosed"]["res"])
+    st, off, out = my_cpp.filter_grasp_pose_raw(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], True, False, so, p1, se, p2,
+                                                sdf_mode=mode, split_status=True)
+    rst, roff, rout = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], True, False, mode, g["open"], p1,
+                                            g["enclosed"], p2, split=True)
+    assert np.array_equal(st, rst) and np.array_equal(off, roff) and np.array_equal(out.view(np.uint32), rout.view(np.uint32))
+    assert (st == 3).any() and (st == 4).any() and (st == 0).any() and (st == 1).any()
+    st0, _, out0 = my_cpp.filter_grasp_pose_raw(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], True, False, so, p1, se, p2,
+                                                sdf_mode=mode)
+    assert np.array_equal(st0 == 0, st == 0) and np.array_equal(st0[st0 != 0] == 1, st[st != 0] == 1)
+    assert not (st0 == 4).any() and np.array_equal(out0.view(np.uint32), out.view(np.uint32))
+    # with pose adjustment the reference counts every collision rejection as "open" (common.cpp:290-294)
+    sta, _, _ = my_cpp.filter_grasp_pose_raw(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], True, True, so, p1, se, p2,
+                                             sdf_mode=mode, split_status=True)
+    assert not (sta == 4).any()
+    if mode == 0:
+        my_cpp.register_gripper_sdf(g["open"]["V"], g["open"]["F"], so)
+        my_cpp.register_gripper_sdf(g["enclosed"]["V"], g["enclosed"]["F"], se)
+        capsys.readouterr()
+        got = my_cpp.filterGraspPose(list(poses), list(sym), nocs_pose, c2n, np.eye(4), np.eye(4), g["gripper_in_grasp"], True,
+                                     False, False, np.zeros(7), np.zeros(7), g["open"]["V"], g["open"]["F"], g["enclosed"]["V"],
+                                     g["enclosed"]["F"], p1, p2, 0.0005, True)
+        line = capsys.readouterr().out.strip().splitlines()[-1]
+        assert line == "n_approach_dir_rej={}, n_ik_rej=0, n_open_gripper_rej={}, n_close_gripper_rej={}".format(
+            int((st == 1).sum()), int((st == 3).sum()), int((st == 4).sum()))
+        assert len(got) == int((st == 0).sum())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
 def test_filter_voxel_margin_bit_exact_vs_oracle(cuda, mode):
     """sdf_margin = octo_resolution * sqrt(3)/2 (the conservative stand-in for the reference's mesh-vs-voxel test):
     GPU == oracle bit for bit, strictly more rejections than the plain SDF predicate, and the reference-facing

@@ -25,6 +25,27 @@ def test_filter_oracle_equals_reference_build(golden_dir, k):
     assert np.array_equal(mine, g_[f"survivors_{k}"])          # same survivors, bit for bit (poses include the winning offset)
 
 
+@pytest.mark.skipif(not mycpp_ref.available(), reason="needs oracle/_ref (the reference's common.cpp, compiled)")
+@pytest.mark.parametrize("k", range(len(mk.FILTER_CASES)))
+@pytest.mark.parametrize("sideways", [0.0, 0.02])
+def test_filter_rejection_counters_equal_reference_build(k, sideways):
+    """The reference's verbose counters (common.cpp:316-319), printed by the compiled reference itself, equal the counts
+    of the oracle's status codes with split=True: 1 approach direction, 3 open gripper, 4 enclosed gripper -- with pose
+    adjustment every collision rejection is an "open" one.  sideways = 2 cm: cases where the open gripper does collide."""
+    S, scale, mode, adjust, fdir = mk.FILTER_CASES[k]
+    (p1, p2, poses, sym, nocs_pose, c2n, g), _ = mk.filter_inputs(S, scale)
+    poses = poses.copy()
+    poses[::3, :3, 3] += poses[::3, :3, 0] * sideways
+    st, off, out = filter_ref.filter_ref(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
+                                         g["enclosed"], p2, split=True)
+    ref, cnt = mycpp_ref.filterGraspPose(poses, sym, nocs_pose, c2n, g["gripper_in_grasp"], fdir, adjust, mode, g["open"], p1,
+                                         g["enclosed"], p2, counters=True)
+    assert cnt == {"approach": int((st == 1).sum()), "ik": 0, "open": int((st == 3).sum()), "close": int((st == 4).sum())}
+    assert len(ref) == int((st == 0).sum())
+    if sideways and not adjust:
+        assert cnt["open"] > 0 and cnt["close"] > 0
+
+
 @pytest.mark.parametrize("k", range(len(mk.OCC_CASES)))
 def test_occupancy_oracle_equals_reference_build(golden_dir, k):
     g_ = np.load(os.path.join(golden_dir, "mycpp_occupancy.npz"))
