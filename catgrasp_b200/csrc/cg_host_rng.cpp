@@ -10,7 +10,12 @@
 // this file restates the generator (MT19937 genrand_int32, numpy/random/src/mt19937) and the two draw loops in C:
 // the caller passes numpy's state in (np.random.get_state()), gets ids for `count` candidates and the advanced
 // state back (np.random.set_state()).  tests/test_abi_and_host.py checks ids AND the post-state against numpy itself.
+#if (defined(__x86_64__) || defined(__i386__)) && !defined(CG_HOST_RNG_SCALAR_ONLY)
+#define CG_X86 1
 #include <immintrin.h>
+#else
+#define CG_X86 0   // e.g. aarch64 (Grace): the scalar walk and replay below
+#endif
 #include <stdint.h>
 #include <string.h>
 #include <time.h>
@@ -99,6 +104,7 @@ int upper_scalar(const uint32_t *w, int avail, uint32_t &i_io, uint32_t &mask_io
   return k;
 }
 
+#if CG_X86
 // ---- AVX2 ---------------------------------------------------------------------------------------------------------
 #define CG_AVX2 __attribute__((target("avx2,popcnt")))
 CG_AVX2 inline __m256i mix8(__m256i a, __m256i b, __m256i far) {
@@ -241,6 +247,8 @@ CG_AVX512 int upper_avx512(const uint32_t *w, int avail, uint32_t &i_io, uint32_
   return k;
 }
 
+#endif   // CG_X86
+
 struct Isa {
   void (*refill)(uint32_t *);
   void (*temper)(const uint32_t *, uint32_t *, int);
@@ -249,11 +257,15 @@ struct Isa {
   int level;
 };
 Isa pick_isa(int force) {
+#if CG_X86
   __builtin_cpu_init();
   int level = __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
   if (force >= 0 && force < level) level = force;
   if (level == 2) return {refill_avx512, temper_avx512, scan_avx512, upper_avx512, 2};
   if (level == 1) return {refill_avx2, temper_avx2, scan_avx2, upper_scalar, 1};
+#else
+  (void)force;
+#endif
   return {refill_scalar, temper_scalar, scan_scalar, upper_scalar, 0};
 }
 Isa g_isa = pick_isa(-1);
@@ -320,7 +332,11 @@ void shuffle_skip(Mt &g, int64_t M) {
 
 inline void backoff(int &spins) {
   if (++spins < 4096) {
+#if CG_X86
     _mm_pause();
+#else
+    std::this_thread::yield();
+#endif
   } else {   // the walker is far behind (or descheduled): stop burning the core
     struct timespec ts = {0, 20000};
     nanosleep(&ts, nullptr);
