@@ -602,7 +602,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": int(h2d * passes),
                     "d2h_bytes_per_step": int(d2h * passes), "passes": e2e_passes, "max_abs_dprob_vs_device_leg": agree,
                     "through": "cg_nunocs_forward_host + cg_graspq_forward_host + cg_filter_grasp_pose_host (C ABI, pinned host buffers, "
-                               "subset ids pre-drawn on the host; the draw-inclusive Python API is in e2e_api)"},
+                               "subset ids pre-drawn on the host; the draw-inclusive Python API is in e2e_api)",
+                    "note": "every pass moves its inputs host->device and its results back inside the timed wall clock; the pinned "
+                            "index buffer (the bulk of h2d_bytes) is read IN PLACE over the link by the three trunk launches "
+                            "(3x its size crosses the link, hidden under the kernels) instead of being copied first; this leg has "
+                            "no L2 flush (its inputs arrive from the host every pass) and a shorter region than `value` "
+                            "(less time at the power cap), so it can come out above the device-resident figure"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
             "flop_per_candidate": FLOP_PER_CAND.get(N), "checksum": checksum, "fp16_clamp_seen": bool(overflow)}
     if alt is not None:

@@ -297,12 +297,24 @@ extern "C" int cg_graspq_forward_host(cg_net *net, const double *cloud_xyz, cons
   CG_CUDA(ctx, cudaMemcpyAsync(d_xyz, cloud_xyz, (size_t)M * 24, cudaMemcpyHostToDevice, st));
   CG_CUDA(ctx, cudaMemcpyAsync(d_nrm, cloud_nrm, (size_t)M * 24, cudaMemcpyHostToDevice, st));
   CG_CUDA(ctx, cudaMemcpyAsync(d_pose, poses, (size_t)B * 128, cudaMemcpyHostToDevice, st));
-  CG_CUDA(ctx, cudaMemcpyAsync(d_ids, ids, (size_t)B * N * 4, cudaMemcpyHostToDevice, st));
+  // The subset indices are the bulk of the input (4 B x N per candidate; 16.8 MB for 4096 x 1024).  When the caller's
+  // buffer is pinned (page-locked, mapped under UVA) the trunk kernels read it in place: every index is fetched exactly
+  // once per trunk launch, two tiles ahead of its use, so the PCIe / C2C transfer hides under the kernels instead of
+  // sitting in front of them.  Pageable memory takes the staged copy.
+  const int32_t *ids_dev = d_ids;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ids) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr)
+      ids_dev = static_cast<const int32_t *>(at.devicePointer);
+    else
+      cudaGetLastError();   // an unregistered pointer is not an error here
+  }
+  if (ids_dev == d_ids) CG_CUDA(ctx, cudaMemcpyAsync(d_ids, ids, (size_t)B * N * 4, cudaMemcpyHostToDevice, st));
   if (mean && stdv) {
     CG_CUDA(ctx, cudaMemcpyAsync(d_mean, mean, 48, cudaMemcpyHostToDevice, st));
     CG_CUDA(ctx, cudaMemcpyAsync(d_std, stdv, 48, cudaMemcpyHostToDevice, st));
   }
-  rc = cg_graspq_forward_dev(net, d_xyz, d_nrm, M, d_pose, B, d_ids, N, mean ? d_mean : nullptr,
+  rc = cg_graspq_forward_dev(net, d_xyz, d_nrm, M, d_pose, B, ids_dev, N, mean ? d_mean : nullptr,
                              stdv ? d_std : nullptr, d_probs, d_label);
   if (rc) return rc;
   CG_CUDA(ctx, cudaMemcpyAsync(out_probs, d_probs, (size_t)B * n_out * 4, cudaMemcpyDeviceToHost, st));
